@@ -1,0 +1,183 @@
+/*
+ * pil.h -- C ABI of the B200-native physics-prior loss ("pil") library.
+ *
+ * This is the drop-in boundary for the hot path of seemapoudel58/Physics_informed_image_segmentation:
+ * the Stage II loss  L = wd*Dice + wb*BCE + lambda_rd*mean((D lap(u) + u(1-u)(u-a))^2)
+ *                        + lambda_pf*mean((eps/2)|grad u|^2 + u^2(1-u)^2/eps)
+ * evaluated forward and backward on single-channel probability maps.
+ *
+ * The reference has no FFI of its own (it is pure Python/PyTorch); the entry points below are what a
+ * binding for this path binds.  Each one cites the reference interface it replaces
+ * (file:line relative to the reference checkout).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *  - All tensor pointers are DEVICE pointers to contiguous (B,1,H,W) == (B,H,W) row-major maps,
+ *    except in the pil_session_* calls, which take HOST pointers.
+ *  - `stream` is a cudaStream_t passed as void*.  Every call is stream-ordered, allocates nothing,
+ *    never synchronises the host (except pil_session_run, which returns the loss to the host) and is
+ *    re-entrant across streams as long as each stream uses its own workspace.
+ *  - Return value: PIL_OK (0), a negative PilStatus, or a positive cudaError_t.
+ *  - There is no CPU fallback: without a CUDA device every compute call fails with a cudaError_t.
+ */
+#ifndef PIL_H_
+#define PIL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIL_VERSION 100 /* 0.1.0 */
+
+/* Number of doubles in a sums vector (see pil_forward). */
+#define PIL_NSUMS 8
+/* Number of floats in a loss-report vector (see pil_finalize). */
+#define PIL_NOUT 8
+
+typedef enum PilStatus {
+    PIL_OK = 0,
+    PIL_ERR_NULL = -1,        /* a required pointer is NULL */
+    PIL_ERR_SHAPE = -2,       /* B<1, H<2 or W<2 (reflect padding needs >= 2, src/pde.py:67) */
+    PIL_ERR_DTYPE = -3,       /* unsupported dtype combination */
+    PIL_ERR_KIND = -4,        /* unknown input kind */
+    PIL_ERR_WORKSPACE = -5,   /* workspace too small or misaligned */
+    PIL_ERR_DIFFUSION = -6,   /* diffusion_coeff <= 0        (ValueError at src/pde.py:14-15) */
+    PIL_ERR_THRESHOLD = -7,   /* reaction_threshold not in (0,1) (ValueError at src/pde.py:16-17) */
+    PIL_ERR_EPSILON = -8,     /* epsilon <= 0 while phase_field_weight > 0 (src/pde.py:199-200) */
+    PIL_ERR_ALIGNMENT = -9,   /* a pointer is not aligned to its element size */
+    PIL_ERR_SESSION = -10     /* session misuse (batch larger than created for, ...) */
+} PilStatus;
+
+typedef enum PilDtype {
+    PIL_F32 = 0,  /* predictions / logits / targets / gradient */
+    PIL_BF16 = 1, /* predictions / logits / targets / gradient (math stays fp32) */
+    PIL_U8 = 2    /* targets only: {0,1} masks */
+} PilDtype;
+
+/* What `x` holds.  The reference applies the activation inside UNet.forward (src/unet.py:208-214)
+ * and hands probabilities to the loss; fusing it is the "logits" entry. */
+typedef enum PilInputKind {
+    PIL_X_PROB = 0,           /* x = u in [0,1]; backward writes dL/du  (strict drop-in, src/loss.py:114) */
+    PIL_X_LOGITS_SIGMOID = 1, /* x = z, u = sigmoid(z); backward writes dL/dz (src/unet.py:210) */
+    PIL_X_LOGITS_TANH = 2     /* x = z, u = (tanh(z)+1)/2; backward writes dL/dz (src/unet.py:211-214) */
+} PilInputKind;
+
+/* The knobs of DiceBCEPDELoss.__init__ (src/loss.py:86-96), same meaning, as Python floats (double).
+ * CLI: --pde-weight, --phase-field-weight, --diffusion-coeff, --reaction-threshold, --epsilon
+ * (main.py:14-43).  A weight of exactly 0 (or less) switches its term off entirely, like the Python
+ * `> 0` gates at src/loss.py:150 and :155. */
+typedef struct PilParams {
+    double dice_weight;
+    double bce_weight;
+    double pde_weight;
+    double phase_field_weight;
+    double diffusion_coeff;
+    double reaction_threshold;
+    double epsilon;
+    double smooth;
+} PilParams;
+
+int pil_version(void);
+const char* pil_status_string(int status);
+
+/* Constructor-time and call-time validation of the reference (src/pde.py:14-17, :199-200). */
+int pil_validate_params(const PilParams* p);
+
+/* Scratch the forward kernel needs for its deterministic two-level reduction.  The caller owns it,
+ * must zero it once (pil_workspace_init or cudaMemset) and may reuse it call after call on the same
+ * stream; the kernel leaves it zeroed where it must be. */
+size_t pil_workspace_bytes(int64_t B, int64_t H, int64_t W);
+int pil_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Forward: ONE fused kernel.  Replaces DiceBCEPDELoss.forward / DiceBCELoss.forward
+ * (src/loss.py:114-162, :36-68) including PDERegularization.compute_loss (src/pde.py:124-145) and
+ * compute_phase_field_loss (src/pde.py:180-212), and -- for the logits kinds -- the model's output
+ * activation (src/unet.py:208-214).
+ *
+ * sums (device, PIL_NSUMS doubles, overwritten) for THIS shard of images:
+ *   [0] I = sum u*t   [1] P = sum u   [2] T = sum t                    (src/loss.py:134-137)
+ *   [3] sum of BCE terms with the log clamp at -100                       (nn.BCELoss, src/loss.py:141)
+ *   [4] sum r^2, r = D*lap(u) + u(1-u)(u-a)                               (src/pde.py:117-120,:143)
+ *   [5] sum (eps/2)(gx^2+gy^2) + u^2(1-u)^2/eps                           (src/pde.py:203-210)
+ *   [6] number of u outside [0,1] or NaN (nn.BCELoss raises on those)
+ *   [7] number of pixels B*H*W
+ * Under data parallelism the caller all-reduces (SUM) `sums` across ranks and passes the result to
+ * pil_finalize / pil_backward.  If loss_out != NULL the kernel also finalises on the spot as if this
+ * shard were the whole batch (single-GPU fast path; same layout as pil_finalize).
+ */
+int pil_forward(const void* x, const void* t, int64_t B, int64_t H, int64_t W,
+                int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                double* sums, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Assemble the scalar loss from (all-reduced) sums on the device: src/loss.py:134-160.
+ * n_global <= 0 means "use sums[7]".
+ * loss_out (device, PIL_NOUT floats): [0] total  [1] dice_loss  [2] bce  [3] L_rd  [4] L_pf
+ * [5] n_invalid  [6],[7] reserved.  [1..4] are the four quantities train_epoch re-computes for
+ * logging at src/train.py:120-150, served here without a second pass over the maps.
+ */
+int pil_finalize(const double* sums, int64_t n_global, const PilParams* p, float* loss_out, void* stream);
+
+/*
+ * Backward: ONE fused kernel writing grad = upstream * grad_scale * dL/dx (same dtype as x).
+ * Replaces autograd through src/loss.py:114-162 / src/pde.py (ConvolutionBackward x3,
+ * ReflectionPad2dBackward x2, BinaryCrossEntropyBackward with its 1e-12 clamp, ...)
+ * and, for the logits kinds, SigmoidBackward/TanhBackward of src/unet.py:208-214.
+ * global_sums: device, the all-reduced sums of pil_forward; n_global: pixels in the GLOBAL batch, or
+ * <= 0 to use the all-reduced count global_sums[7] on the device (unequal shards, no host sync).
+ * upstream: device pointer to the scalar float gradient of the loss (NULL = 1.0), read on the device
+ * so that loss.backward() needs no host sync.  grad_scale: host scalar (world_size correction under
+ * DDP-style gradient averaging).
+ */
+int pil_backward(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W,
+                 int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                 const double* global_sums, int64_t n_global, const float* upstream, float grad_scale,
+                 void* stream);
+
+/*
+ * The PDERegularization operators a caller can use on their own (fp32 maps):
+ *   pil_laplacian            compute_laplacian              src/pde.py:49-79
+ *   pil_laplacian_adjoint    its autograd backward (transpose of the reflect-Laplacian)
+ *   pil_reaction             reaction_term                  src/pde.py:81-99
+ *   pil_grad_mag_sq          compute_gradient_magnitude     src/pde.py:147-178
+ *   pil_grad_mag_sq_backward its autograd backward: out = J^T (g), J the Jacobian at u
+ */
+int pil_laplacian(const float* u, float* out, int64_t B, int64_t H, int64_t W, void* stream);
+int pil_laplacian_adjoint(const float* g, float* out, int64_t B, int64_t H, int64_t W, void* stream);
+int pil_reaction(const float* u, float* out, int64_t n, double reaction_threshold, void* stream);
+int pil_grad_mag_sq(const float* u, float* out, int64_t B, int64_t H, int64_t W, void* stream);
+int pil_grad_mag_sq_backward(const float* u, const float* g, float* out, int64_t B, int64_t H, int64_t W,
+                             void* stream);
+
+/*
+ * Host-buffer session: the end-to-end call for a caller whose maps live in HOST memory (pinned for
+ * full speed).  One pil_session_run = H2D of x and t (chunked, overlapped with the forward kernel),
+ * forward, backward (chunked, overlapped with the D2H of the gradient), D2H of the loss report.
+ * It is what `loss = criterion(outputs, masks); loss.backward()` (src/train.py:117,:163) is to a
+ * host-side caller.  grad_host may be NULL (loss only).  loss_out_host: PIL_NOUT floats.
+ */
+typedef struct PilSession PilSession;
+int pil_session_create(PilSession** out, int device, int64_t max_B, int64_t H, int64_t W,
+                       int x_dtype, int t_dtype);
+int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B,
+                    int x_kind, const PilParams* p, float* loss_out_host);
+int pil_session_destroy(PilSession* s);
+
+/* Introspection for tests/benchmarks: how the last launch on this thread was tiled. */
+typedef struct PilLaunchInfo {
+    int32_t fwd_blocks, fwd_threads, fwd_rows_per_segment, fwd_aligned;
+    int32_t bwd_blocks, bwd_threads, bwd_rows_per_segment, bwd_aligned;
+    int64_t kernels_launched; /* running count of kernels this library launched in this process */
+} PilLaunchInfo;
+int pil_last_launch_info(PilLaunchInfo* out);
+
+/* Tuning override for benchmarks (0 = automatic): rows per segment for fwd / bwd. */
+int pil_set_tuning(int fwd_rows_per_segment, int bwd_rows_per_segment);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIL_H_ */

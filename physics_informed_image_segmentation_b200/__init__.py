@@ -1,0 +1,19 @@
+"""B200-native physics-prior segmentation loss: a drop-in for the hot path of
+seemapoudel58/Physics_informed_image_segmentation (src/pde.py + src/loss.py + the loss call of
+src/train.py), implemented as hand-written sm_100a CUDA kernels behind a C ABI (include/pil.h).
+
+The names re-exported here are the ones the reference's `src/__init__.py:3-4` exports for this path.
+"""
+from .loss import DiceBCELoss, DiceBCEPDELoss
+from .pde import PDERegularization, create_pde_regularization
+from .functional import LossParams
+from .sharding import shard_bounds, all_reduce_sums, loss_report_from_sums
+from .session import HostSession
+from .integration import install_into_reference, use_logits_head
+
+__all__ = [
+    "DiceBCELoss", "DiceBCEPDELoss", "PDERegularization", "create_pde_regularization", "LossParams",
+    "shard_bounds", "all_reduce_sums", "loss_report_from_sums", "HostSession",
+    "install_into_reference", "use_logits_head",
+]
+__version__ = "0.1.0"

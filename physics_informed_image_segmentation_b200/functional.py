@@ -1,0 +1,329 @@
+"""Torch-tensor level wrappers over the C ABI (include/pil.h) and the autograd glue.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); every arithmetic pass over the
+maps happens inside libpil.so.  CUDA tensors only -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, replace
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import F32, BF16, U8, X_PROB, X_LOGITS_SIGMOID, X_LOGITS_TANH, PIL_NOUT, PIL_NSUMS, PilParams
+
+OUT_TOTAL, OUT_DICE, OUT_BCE, OUT_RD, OUT_PF, OUT_INVALID = 0, 1, 2, 3, 4, 5
+
+_ACTIVATION_KIND = {"none": X_PROB, "prob": X_PROB, "sigmoid": X_LOGITS_SIGMOID, "tanh": X_LOGITS_TANH}
+
+
+@dataclass(frozen=True)
+class LossParams:
+    """Knobs of DiceBCEPDELoss.__init__ (reference src/loss.py:86-96), same names and defaults."""
+    dice_weight: float = 0.5
+    bce_weight: float = 0.5
+    pde_weight: float = 1e-3
+    phase_field_weight: float = 0.0
+    smooth: float = 1e-6
+    diffusion_coeff: float = 1.0
+    reaction_threshold: float = 0.5
+    epsilon: float = 0.05
+
+    def c(self) -> PilParams:
+        return PilParams(float(self.dice_weight), float(self.bce_weight), float(self.pde_weight),
+                         float(self.phase_field_weight), float(self.diffusion_coeff),
+                         float(self.reaction_threshold), float(self.epsilon), float(self.smooth))
+
+    def validate(self) -> None:
+        """Same exceptions, same messages, same order as the reference (src/pde.py:14-17, :199-200)."""
+        if self.diffusion_coeff <= 0:
+            raise ValueError("diffusion_coeff must be positive")
+        if not (0 < self.reaction_threshold < 1):
+            raise ValueError("reaction_threshold must be in (0,1)")
+        if self.phase_field_weight > 0 and self.epsilon <= 0:
+            raise ValueError("epsilon must be positive")
+
+
+def activation_kind(name: str) -> int:
+    try:
+        return _ACTIVATION_KIND[name.lower()]
+    except KeyError:
+        raise ValueError(f"Unsupported output_activation: {name}. Must be 'sigmoid' or 'tanh'") from None
+
+
+def _x_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"predictions must be float32 or bfloat16, got {t.dtype}")
+
+
+def _t_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype in (torch.uint8, torch.bool):
+        return U8
+    raise TypeError(f"targets must be float32, bfloat16, uint8 or bool, got {t.dtype}")
+
+
+def _bhw(x: torch.Tensor) -> Tuple[int, int, int]:
+    if x.dim() == 4:
+        if x.shape[1] != 1:
+            # the reference's stencils are (1,1,3,3) conv kernels (src/pde.py:45-47): C != 1 raises there too
+            raise RuntimeError(f"expected single-channel maps (B,1,H,W), got {tuple(x.shape)}")
+        return x.shape[0], x.shape[2], x.shape[3]
+    if x.dim() == 3:
+        return x.shape[0], x.shape[1], x.shape[2]
+    raise RuntimeError(f"expected (B,1,H,W) or (B,H,W) maps, got {tuple(x.shape)}")
+
+
+def check_maps(x: torch.Tensor, t: Optional[torch.Tensor]) -> Tuple[int, int, int]:
+    if not x.is_cuda:
+        raise RuntimeError("physics_informed_image_segmentation_b200 runs on CUDA tensors only (no CPU fallback); "
+                           f"got a tensor on {x.device}")
+    if not x.is_contiguous():
+        # reference: predictions.view(-1) (src/loss.py:130) raises on non-contiguous input
+        raise RuntimeError("view size is not compatible with input tensor's size and stride: "
+                           "predictions must be contiguous (reference src/loss.py:130 uses .view(-1))")
+    B, H, W = _bhw(x)
+    if H < 2 or W < 2:
+        raise RuntimeError("reflect padding needs H >= 2 and W >= 2 (reference src/pde.py:67)")
+    if t is not None:
+        if t.shape != x.shape:
+            raise ValueError(f"Using a target size ({tuple(t.shape)}) that is different to the input size "
+                             f"({tuple(x.shape)}) is deprecated. Please ensure they have the same size.")
+        if t.device != x.device:
+            raise RuntimeError(f"targets on {t.device}, predictions on {x.device}")
+        if not t.is_contiguous():
+            raise RuntimeError("targets must be contiguous (reference src/loss.py:131 uses .view(-1))")
+    return B, H, W
+
+
+# ---------------------------------------------------------------------------------------------
+# workspace cache: one zero-initialised scratch buffer per (device, stream)
+# ---------------------------------------------------------------------------------------------
+_WORKSPACES = {}
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def workspace(device: torch.device, B: int, H: int, W: int) -> torch.Tensor:
+    need = _lib.lib().pil_workspace_bytes(B, H, W)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device))
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+# ---------------------------------------------------------------------------------------------
+# raw calls
+# ---------------------------------------------------------------------------------------------
+def forward_sums(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, sums: Optional[torch.Tensor] = None,
+                 report: Optional[torch.Tensor] = None, finalize: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """K1.  Returns (sums float64[8], report float32[8] or None).  With finalize=True the kernel's last
+    block also assembles the loss as if this shard were the whole batch (single-GPU fast path)."""
+    B, H, W = check_maps(x, t)
+    L = _lib.lib()
+    dev = x.device
+    if sums is None:
+        sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    if finalize and report is None:
+        report = torch.empty(PIL_NOUT, dtype=torch.float32, device=dev)
+    ws = workspace(dev, B, H, W)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = L.pil_forward(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind, ctypes.byref(cp),
+                           sums.data_ptr(), report.data_ptr() if finalize else None, ws.data_ptr(), ws.numel(),
+                           _stream_ptr(dev))
+    _lib.check(st, "pil_forward")
+    return sums, (report if finalize else None)
+
+
+def finalize_report(sums: torch.Tensor, n_global: int, p: LossParams, report: Optional[torch.Tensor] = None) -> torch.Tensor:
+    L = _lib.lib()
+    dev = sums.device
+    if report is None:
+        report = torch.empty(PIL_NOUT, dtype=torch.float32, device=dev)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = L.pil_finalize(sums.data_ptr(), int(n_global), ctypes.byref(cp), report.data_ptr(), _stream_ptr(dev))
+    _lib.check(st, "pil_finalize")
+    return report
+
+
+def backward_grad(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, gsums: torch.Tensor, n_global: int,
+                  upstream: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K2.  grad = upstream * grad_scale * dL/dx, same dtype/shape as x."""
+    B, H, W = check_maps(x, t)
+    L = _lib.lib()
+    dev = x.device
+    if out is None:
+        out = torch.empty_like(x)
+    up_ptr = None
+    if upstream is not None:
+        if upstream.dtype != torch.float32 or upstream.numel() != 1 or upstream.device != dev:
+            upstream = upstream.to(device=dev, dtype=torch.float32).reshape(1)
+        up_ptr = upstream.data_ptr()
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = L.pil_backward(x.data_ptr(), t.data_ptr(), out.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                            ctypes.byref(cp), gsums.data_ptr(), int(n_global), up_ptr, float(grad_scale),
+                            _stream_ptr(dev))
+    _lib.check(st, "pil_backward")
+    return out
+
+
+def launch_info() -> _lib.PilLaunchInfo:
+    info = _lib.PilLaunchInfo()
+    _lib.check(_lib.lib().pil_last_launch_info(ctypes.byref(info)), "pil_last_launch_info")
+    return info
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd glue
+# ---------------------------------------------------------------------------------------------
+class _FusedLossFn(torch.autograd.Function):
+    """loss-report = K1(x, t) [-> all-reduce] ; dL/dx = K2(x, t, global sums).
+
+    Returns the whole report vector (float32[8]); callers index the entry they want, so one forward
+    serves the total loss AND the four logged components (reference src/train.py:120-150)."""
+
+    @staticmethod
+    def forward(ctx, x, t, p: LossParams, kind: int, which: int, group, ddp_average: bool):
+        x_d = x.detach()
+        t_d = t.detach()
+        distributed = group is not None
+        if distributed:
+            import torch.distributed as dist
+
+            sums, _ = forward_sums(x_d, t_d, p, kind, finalize=False)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            n_global = -1  # read the all-reduced pixel count sums[7] on the device
+            report = finalize_report(sums, n_global, p)
+            scale = float(dist.get_world_size(group)) if ddp_average else 1.0
+        else:
+            sums, report = forward_sums(x_d, t_d, p, kind, finalize=True)
+            n_global = x_d.numel()
+            scale = 1.0
+        ctx.save_for_backward(x_d, t_d, sums)
+        ctx.p, ctx.kind, ctx.which, ctx.n_global, ctx.scale = p, kind, which, n_global, scale
+        ctx.mark_non_differentiable(report)
+        return report[which], report
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_report):
+        x, t, sums = ctx.saved_tensors
+        p = ctx.p
+        # differentiate the requested entry only: the total, or one component on its own
+        if ctx.which == OUT_DICE:
+            p = replace(p, dice_weight=1.0, bce_weight=0.0, pde_weight=0.0, phase_field_weight=0.0)
+        elif ctx.which == OUT_BCE:
+            p = replace(p, dice_weight=0.0, bce_weight=1.0, pde_weight=0.0, phase_field_weight=0.0)
+        elif ctx.which == OUT_RD:
+            p = replace(p, dice_weight=0.0, bce_weight=0.0, pde_weight=1.0, phase_field_weight=0.0)
+        elif ctx.which == OUT_PF:
+            p = replace(p, dice_weight=0.0, bce_weight=0.0, pde_weight=0.0, phase_field_weight=1.0)
+        grad = backward_grad(x, t, p, ctx.kind, sums, ctx.n_global, upstream=g_loss, grad_scale=ctx.scale)
+        return grad, None, None, None, None, None, None
+
+
+def fused_loss(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int = X_PROB, which: int = OUT_TOTAL,
+               group=None, ddp_average: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(requested scalar with grad_fn, detached report float32[8])."""
+    p.validate()
+    check_maps(x, t)
+    if x.requires_grad and torch.is_grad_enabled():
+        return _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average)
+    # no graph needed (validation / logging): skip the autograd.Function overhead
+    if group is not None:
+        import torch.distributed as dist
+
+        sums, _ = forward_sums(x.detach(), t.detach(), p, kind, finalize=False)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        report = finalize_report(sums, -1, p)
+    else:
+        _, report = forward_sums(x.detach(), t.detach(), p, kind, finalize=True)
+    return report[which], report
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone stencil operators (PDERegularization methods)
+# ---------------------------------------------------------------------------------------------
+def _stencil_call(name: str, *tensors: torch.Tensor) -> torch.Tensor:
+    u = tensors[0]
+    B, H, W = check_maps(u, None)
+    if u.dtype != torch.float32:
+        raise TypeError(f"{name} works on float32 maps, got {u.dtype}")
+    out = torch.empty_like(u)
+    fn = getattr(_lib.lib(), name)
+    with torch.cuda.device(u.device):
+        st = fn(*[t.data_ptr() for t in tensors], out.data_ptr(), B, H, W, _stream_ptr(u.device))
+    _lib.check(st, name)
+    return out
+
+
+class _LaplacianFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u):
+        return _stencil_call("pil_laplacian", u.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        return _stencil_call("pil_laplacian_adjoint", g.contiguous())
+
+
+class _GradMagSqFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u):
+        ctx.save_for_backward(u.detach())
+        return _stencil_call("pil_grad_mag_sq", u.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        (u,) = ctx.saved_tensors
+        return _stencil_call("pil_grad_mag_sq_backward", u, g.contiguous())
+
+
+class _ReactionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, a: float):
+        ud = u.detach()
+        if not ud.is_cuda:
+            raise RuntimeError("CUDA tensors only (no CPU fallback)")
+        if ud.dtype != torch.float32 or not ud.is_contiguous():
+            raise TypeError("reaction_term works on contiguous float32 maps")
+        out = torch.empty_like(ud)
+        with torch.cuda.device(ud.device):
+            st = _lib.lib().pil_reaction(ud.data_ptr(), out.data_ptr(), ud.numel(), float(a), _stream_ptr(ud.device))
+        _lib.check(st, "pil_reaction")
+        ctx.save_for_backward(ud)
+        ctx.a = float(a)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (u,) = ctx.saved_tensors
+        a = ctx.a
+        return g * (u * (2.0 * (1.0 + a) - 3.0 * u) - a), None  # f'(u) = -3u^2 + 2(1+a)u - a
+
+
+def laplacian(u: torch.Tensor) -> torch.Tensor:
+    return _LaplacianFn.apply(u)
+
+
+def grad_mag_sq(u: torch.Tensor) -> torch.Tensor:
+    return _GradMagSqFn.apply(u)
+
+
+def reaction(u: torch.Tensor, a: float) -> torch.Tensor:
+    return _ReactionFn.apply(u, a)

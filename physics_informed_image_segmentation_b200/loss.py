@@ -1,0 +1,140 @@
+"""Drop-in for the reference's src/loss.py: DiceBCELoss and DiceBCEPDELoss with the same constructor
+signatures, attribute surface and call convention, backed by the two fused sm_100a kernels.
+
+    criterion = DiceBCEPDELoss(dice_weight=0.5, bce_weight=0.5, pde_weight=1e-4, phase_field_weight=1e-4,
+                               diffusion_coeff=5.0, reaction_threshold=0.5, epsilon=0.05).to(device)
+    loss = criterion(outputs, masks)      # outputs: probabilities (B,1,H,W), exactly like src/train.py:117
+    loss.backward()                       # one fused backward kernel writes dL/d(outputs)
+
+Extra (not in the reference): `forward_logits(logits, masks, activation="sigmoid"|"tanh")` fuses the
+model's output activation (src/unet.py:208-214) into both kernels and returns dL/dlogits, and
+`process_group=` shards the batch over ranks with one 64-byte all-reduce of the partial sums.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .functional import LossParams
+from .pde import PDERegularization
+
+
+class _FusedBCE(nn.Module):
+    """Stands where the reference keeps `self.bce = nn.BCELoss()` (src/loss.py:34, :112): callers invoke
+    `criterion.bce(outputs, masks)` for logging (src/train.py:135, :238)."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = weakref.ref(owner)
+
+    def forward(self, predictions: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        owner = self._owner()
+        if owner is not None and not (torch.is_grad_enabled() and predictions.requires_grad):
+            cached = owner._cached_component(predictions, Fn.OUT_BCE, None, targets)
+            if cached is not None:
+                return cached
+        p = LossParams(dice_weight=0.0, bce_weight=1.0, pde_weight=0.0, phase_field_weight=0.0)
+        out, _ = Fn.fused_loss(predictions, targets, p, Fn.X_PROB, Fn.OUT_BCE)
+        return out
+
+
+class _FusedLossBase(nn.Module):
+    def _init_runtime(self, process_group, ddp_average: bool):
+        self.process_group = process_group
+        self.ddp_average = ddp_average
+        self._last = None  # (key, report) of the most recent fused forward
+        self.last_report: Optional[torch.Tensor] = None
+
+    def _params(self) -> LossParams:
+        raise NotImplementedError
+
+    def _run(self, x: torch.Tensor, t: torch.Tensor, kind: int) -> torch.Tensor:
+        p = self._params()
+        loss, report = Fn.fused_loss(x, t, p, kind, Fn.OUT_TOTAL, self.process_group, self.ddp_average)
+        self.last_report = report
+        # identity (weak) + version counter: a different tensor that merely reuses the address never hits
+        self._last = (weakref.ref(x), x._version, weakref.ref(t), t._version, kind, p, report)
+        return loss
+
+    def _cached_component(self, x: torch.Tensor, which: int, epsilon, t: Optional[torch.Tensor] = None):
+        """Component `which` of the last fused forward if it was evaluated on exactly this tensor
+        (same storage, same version counter) with the same physics knobs; else None."""
+        if self._last is None:
+            return None
+        wx, vx, wt, vt, kind, p, report = self._last
+        if kind != Fn.X_PROB or wx() is not x or x._version != vx:
+            return None
+        if t is not None and (wt() is not t or t._version != vt):
+            return None
+        if which == Fn.OUT_PF and (epsilon is None or float(epsilon) != float(p.epsilon)):
+            return None
+        return report[which]
+
+    def components(self) -> dict:
+        """Loss terms of the most recent forward (device scalars, no sync): what src/train.py:120-150
+        recomputes with a second pass."""
+        if self.last_report is None:
+            raise RuntimeError("no forward pass has run yet")
+        r = self.last_report
+        return {"loss": r[0], "dice_loss": r[1], "bce_loss": r[2], "pde_loss": r[3], "phase_field_loss": r[4]}
+
+    def forward(self, predictions: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        return self._run(predictions, targets, Fn.X_PROB)
+
+    def forward_logits(self, logits: torch.Tensor, targets: torch.Tensor, activation: str = "sigmoid") -> torch.Tensor:
+        """Same loss evaluated on activation(logits) with the activation fused into the kernels; the
+        backward kernel then writes dL/dlogits directly (replaces src/unet.py:208-214 + SigmoidBackward)."""
+        return self._run(logits, targets, Fn.activation_kind(activation))
+
+
+class DiceBCELoss(_FusedLossBase):
+    """Batch-global soft Dice + mean BCE (reference src/loss.py:7-68)."""
+
+    def __init__(self, dice_weight: float = 0.5, bce_weight: float = 0.5, smooth: float = 1e-6,
+                 process_group=None, ddp_average: bool = True):
+        super().__init__()
+        self.dice_weight = dice_weight
+        self.bce_weight = bce_weight
+        self.smooth = smooth
+        self.bce = _FusedBCE(self)
+        self._init_runtime(process_group, ddp_average)
+
+    def _params(self) -> LossParams:
+        return LossParams(dice_weight=self.dice_weight, bce_weight=self.bce_weight, pde_weight=0.0,
+                          phase_field_weight=0.0, smooth=self.smooth)
+
+
+class DiceBCEPDELoss(_FusedLossBase):
+    """Dice + BCE + lambda_rd * RD residual + lambda_pf * phase-field energy (reference src/loss.py:71-162).
+
+    The weights are read at call time (plain attributes, as in the reference), `pde_weight > 0` and
+    `phase_field_weight > 0` gate their terms (src/loss.py:150, :155), epsilon is validated only when
+    the phase-field term is active (src/pde.py:199-200)."""
+
+    def __init__(self, dice_weight: float = 0.5, bce_weight: float = 0.5, pde_weight: float = 1e-3,
+                 phase_field_weight: float = 0.0, smooth: float = 1e-6, diffusion_coeff: float = 1.0,
+                 reaction_threshold: float = 0.5, epsilon: float = 0.05,
+                 process_group=None, ddp_average: bool = True):
+        super().__init__()
+        self.dice_weight = dice_weight
+        self.bce_weight = bce_weight
+        self.pde_weight = pde_weight
+        self.phase_field_weight = phase_field_weight
+        self.smooth = smooth
+        self.epsilon = epsilon
+        self.pde_regularization = PDERegularization(diffusion_coeff=diffusion_coeff,
+                                                    reaction_threshold=reaction_threshold)
+        self.pde_regularization._owner = weakref.ref(self)
+        self.bce = _FusedBCE(self)
+        self._init_runtime(process_group, ddp_average)
+
+    def _params(self) -> LossParams:
+        reg = self.pde_regularization
+        return LossParams(dice_weight=self.dice_weight, bce_weight=self.bce_weight, pde_weight=self.pde_weight,
+                          phase_field_weight=self.phase_field_weight, smooth=self.smooth,
+                          diffusion_coeff=reg.diffusion_coeff, reaction_threshold=reg.reaction_threshold,
+                          epsilon=self.epsilon)

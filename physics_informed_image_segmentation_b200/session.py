@@ -1,0 +1,91 @@
+"""Host-buffer entry point (pil_session_* of include/pil.h): maps in host memory in, loss report and
+gradient in host memory out, with the H2D / kernels / D2H pipeline inside the library."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .functional import LossParams, activation_kind
+
+_NP_X = {np.dtype(np.float32): _lib.F32}
+_NP_T = {np.dtype(np.float32): _lib.F32, np.dtype(np.uint8): _lib.U8}
+
+
+def _host_ptr(a):
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda:
+            raise ValueError("HostSession takes host tensors; use DiceBCEPDELoss for device tensors")
+        if not a.is_contiguous():
+            raise ValueError("host buffers must be contiguous")
+        return a.data_ptr()
+    a = np.ascontiguousarray(a)
+    return a.ctypes.data
+
+
+def _dtype_code(a, is_target: bool) -> int:
+    if isinstance(a, torch.Tensor):
+        if a.dtype == torch.float32:
+            return _lib.F32
+        if a.dtype == torch.bfloat16:
+            return _lib.BF16
+        if is_target and a.dtype in (torch.uint8, torch.bool):
+            return _lib.U8
+        raise TypeError(f"unsupported dtype {a.dtype}")
+    table = _NP_T if is_target else _NP_X
+    try:
+        return table[np.asarray(a).dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {np.asarray(a).dtype}") from None
+
+
+class HostSession:
+    """Owns the device buffers, streams and events for maps of a fixed (max_B, H, W)."""
+
+    def __init__(self, max_batch: int, height: int, width: int, device: int = 0, x_dtype: int = _lib.F32,
+                 t_dtype: int = _lib.F32):
+        self._h = ctypes.c_void_p()
+        self.shape = (int(max_batch), int(height), int(width))
+        self.x_dtype, self.t_dtype = x_dtype, t_dtype
+        st = _lib.lib().pil_session_create(ctypes.byref(self._h), int(device), *self.shape, x_dtype, t_dtype)
+        _lib.check(st, "pil_session_create")
+
+    def run(self, x_host, t_host, params: LossParams, grad_host=None, activation: str = "sigmoid") -> np.ndarray:
+        """One forward+backward.  Returns the loss report (float32[8]: total, dice, bce, rd, pf, ...);
+        the gradient w.r.t. x is written into grad_host when given."""
+        params.validate()
+        if self._h is None:
+            raise RuntimeError("session closed")
+        shp = tuple(x_host.shape)
+        B = shp[0]
+        if shp[-2:] != self.shape[1:] or B > self.shape[0]:
+            raise ValueError(f"maps {shp} do not fit the session {self.shape}")
+        if _dtype_code(x_host, False) != self.x_dtype or _dtype_code(t_host, True) != self.t_dtype:
+            raise TypeError("dtype differs from the session's")
+        out = np.zeros(_lib.PIL_NOUT, dtype=np.float32)
+        cp = params.c()
+        st = _lib.lib().pil_session_run(self._h, _host_ptr(x_host), _host_ptr(t_host),
+                                        _host_ptr(grad_host) if grad_host is not None else None, int(B),
+                                        activation_kind(activation), ctypes.byref(cp), out.ctypes.data)
+        _lib.check(st, "pil_session_run")
+        return out
+
+    def close(self) -> None:
+        if self._h is not None and self._h.value:
+            _lib.lib().pil_session_destroy(self._h)
+        self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,164 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/pil.h declares, the
+host-side mirror of the reference interface (constructors, attributes, errors), argument validation
+of the C ABI that needs no device, and the sharding helpers."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import physics_informed_image_segmentation_b200 as P
+from physics_informed_image_segmentation_b200 import _lib, functional as Fn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "pil.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pil_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"libpil.so does not export {n}"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS)
+    assert L.pil_version() == 100
+    assert b"diffusion_coeff must be positive" == L.pil_status_string(-6)
+
+
+def test_c_abi_validation_needs_no_device():
+    L = _lib.lib()
+    ok = P.LossParams().c()
+    assert L.pil_validate_params(ctypes.byref(ok)) == 0
+    assert L.pil_validate_params(ctypes.byref(P.LossParams(diffusion_coeff=0.0).c())) == -6
+    assert L.pil_validate_params(ctypes.byref(P.LossParams(reaction_threshold=1.0).c())) == -7
+    assert L.pil_validate_params(ctypes.byref(P.LossParams(phase_field_weight=1.0, epsilon=0.0).c())) == -8
+    assert L.pil_validate_params(ctypes.byref(P.LossParams(phase_field_weight=0.0, epsilon=0.0).c())) == 0
+    assert L.pil_workspace_bytes(0, 8, 8) == 0 and L.pil_workspace_bytes(1, 1, 8) == 0
+    assert L.pil_workspace_bytes(64, 1024, 1024) >= 256 + 8 * 8
+    # argument checks come before any CUDA call
+    buf = (ctypes.c_char * 64)()
+    a = ctypes.addressof(buf)
+    assert L.pil_forward(None, a, 1, 8, 8, 0, 0, 0, ctypes.byref(ok), a, None, a, 64, None) == -1
+    assert L.pil_forward(a, a, 1, 1, 8, 0, 0, 0, ctypes.byref(ok), a, None, a, 64, None) == -2
+    assert L.pil_forward(a, a, 1, 8, 8, 7, 0, 0, ctypes.byref(ok), a, None, a, 64, None) == -3
+    assert L.pil_forward(a, a, 1, 8, 8, 0, 0, 9, ctypes.byref(ok), a, None, a, 64, None) == -4
+    assert L.pil_forward(a, a, 1, 8, 8, 0, 0, 0, ctypes.byref(ok), a, None, a, 8, None) == -5
+    assert L.pil_forward(a + 2, a, 1, 8, 8, 0, 0, 0, ctypes.byref(ok), a, None, a, 64, None) == -9
+    assert L.pil_backward(a, a, None, 1, 8, 8, 0, 0, 0, ctypes.byref(ok), a, 64, None, 1.0, None) == -1
+
+
+def test_constructor_signatures_and_defaults_match_reference():
+    """src/loss.py:24-29, :86-96; src/pde.py:7-11"""
+    import inspect
+
+    sig = inspect.signature(P.DiceBCEPDELoss.__init__)
+    want = [("dice_weight", 0.5), ("bce_weight", 0.5), ("pde_weight", 1e-3), ("phase_field_weight", 0.0),
+            ("smooth", 1e-6), ("diffusion_coeff", 1.0), ("reaction_threshold", 0.5), ("epsilon", 0.05)]
+    got = [(k, v.default) for k, v in list(sig.parameters.items())[1:9]]
+    assert got == want
+    sig = inspect.signature(P.DiceBCELoss.__init__)
+    assert [(k, v.default) for k, v in list(sig.parameters.items())[1:4]] == [("dice_weight", 0.5), ("bce_weight", 0.5), ("smooth", 1e-6)]
+    sig = inspect.signature(P.PDERegularization.__init__)
+    assert [(k, v.default) for k, v in list(sig.parameters.items())[1:]] == [("diffusion_coeff", 1.0), ("reaction_threshold", 0.5)]
+
+
+def test_attribute_surface_and_errors():
+    c = P.DiceBCEPDELoss(0.5, 0.5, 1e-4, 1e-4, 1e-6, 5.0, 0.5, 0.05)  # positional, like a caller may
+    assert (c.dice_weight, c.bce_weight, c.pde_weight, c.phase_field_weight, c.smooth, c.epsilon) == (0.5, 0.5, 1e-4, 1e-4, 1e-6, 0.05)
+    assert c.pde_regularization.diffusion_coeff == 5.0 and c.pde_regularization.reaction_threshold == 0.5
+    assert callable(c.bce) and isinstance(c, torch.nn.Module) and isinstance(c.pde_regularization, P.PDERegularization)
+    assert sorted(c.state_dict()) == ["pde_regularization.grad_x_kernel", "pde_regularization.grad_y_kernel",
+                                      "pde_regularization.laplacian_kernel"]
+    assert c.state_dict()["pde_regularization.laplacian_kernel"].shape == (1, 1, 3, 3)
+    assert c.to("cpu") is c
+    with pytest.raises(ValueError, match="diffusion_coeff must be positive"):
+        P.DiceBCEPDELoss(diffusion_coeff=0.0)
+    with pytest.raises(ValueError, match=r"reaction_threshold must be in \(0,1\)"):
+        P.PDERegularization(1.0, 0.0)
+    with pytest.raises(ValueError, match="epsilon must be positive"):
+        P.PDERegularization().compute_phase_field_loss(torch.rand(1, 1, 4, 4), epsilon=0.0)
+    # epsilon <= 0 is accepted at construction, like the reference (only checked when the PF term runs)
+    P.DiceBCEPDELoss(epsilon=-1.0)
+    b = P.DiceBCELoss()
+    assert (b.dice_weight, b.bce_weight, b.smooth) == (0.5, 0.5, 1e-6) and callable(b.bce)
+
+
+def test_no_cpu_fallback():
+    c = P.DiceBCEPDELoss()
+    u = torch.rand(2, 1, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c(u, torch.zeros_like(u))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.PDERegularization().compute_laplacian(u)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        P.PDERegularization().reaction_term(u)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "physics_informed_image_segmentation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_shard_bounds():
+    for B in (0, 1, 5, 8, 64, 67):
+        for W in (1, 2, 3, 8):
+            spans = [P.shard_bounds(B, r, W) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        P.shard_bounds(4, 2, 2)
+
+
+def test_loss_report_from_sums_matches_oracle_finalize():
+    from oracle import pil_oracle as po
+
+    s = np.array([10.0, 30.0, 25.0, 40.0, 3.0, 7.0, 0.0, 100.0])
+    for kw in (dict(), dict(pde_weight=0.0), dict(phase_field_weight=2.0, pde_weight=3.0)):
+        p = P.LossParams(**kw)
+        rep = P.loss_report_from_sums(s, None, p)
+        want = po.finalize(s, 100, po.Params(dice_weight=p.dice_weight, bce_weight=p.bce_weight, pde_weight=p.pde_weight,
+                                             phase_field_weight=p.phase_field_weight, smooth=p.smooth,
+                                             diffusion_coeff=p.diffusion_coeff, reaction_threshold=p.reaction_threshold,
+                                             epsilon=p.epsilon))
+        got = [rep[k] for k in ("loss", "dice_loss", "bce_loss", "pde_loss", "phase_field_loss")]
+        assert np.allclose(got, want, rtol=1e-15, atol=0)
+
+
+def test_install_into_reference_rebinds_names():
+    import sys
+    import types
+
+    pkg = types.ModuleType("fakeref")
+    sub = types.ModuleType("fakeref.train")
+    class Old:  # noqa: E306
+        pass
+    sub.DiceBCEPDELoss = Old
+    sub.DiceBCELoss = Old
+    pkg.PDERegularization = Old
+    sys.modules["fakeref"], sys.modules["fakeref.train"] = pkg, sub
+    try:
+        rep = P.install_into_reference("fakeref")
+        assert sub.DiceBCEPDELoss is P.DiceBCEPDELoss and sub.DiceBCELoss is P.DiceBCELoss
+        assert pkg.PDERegularization is P.PDERegularization and len(rep) == 3
+    finally:
+        del sys.modules["fakeref"], sys.modules["fakeref.train"]
+
+    class M:
+        activation_name = "sigmoid"
+    m = M()
+    with P.use_logits_head(m) as name:
+        assert name == "sigmoid" and m.activation_name == "none"
+    assert m.activation_name == "sigmoid"

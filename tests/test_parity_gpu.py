@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+vectors of the real reference.  Tolerances (BASELINE.json north_star): 1e-5 relative in fp32 for the
+loss, each component and dL/dx (max-norm and L2 relative); 1e-2 for the bf16 input path."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import blob_inputs, iid_inputs, rel_l2, rel_max, rel_scalar
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+KIND_NAME = {"sigmoid": 1, "tanh": 2}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def Fn():
+    from physics_informed_image_segmentation_b200 import functional
+
+    return functional
+
+
+@pytest.fixture(scope="module")
+def po():
+    from oracle import pil_oracle
+
+    return pil_oracle
+
+
+def lp(Fn, p):
+    """oracle Params -> package LossParams"""
+    return Fn.LossParams(dice_weight=p.dice_weight, bce_weight=p.bce_weight, pde_weight=p.pde_weight,
+                         phase_field_weight=p.phase_field_weight, smooth=p.smooth, diffusion_coeff=p.diffusion_coeff,
+                         reaction_threshold=p.reaction_threshold, epsilon=p.epsilon)
+
+
+def gpu_loss_and_grad(Fn, x, t, p, kind):
+    sums, rep = Fn.forward_sums(x, t, p, kind)
+    g = Fn.backward_grad(x, t, p, kind, sums, x.numel())
+    torch.cuda.synchronize()
+    return sums.cpu().numpy(), rep.cpu().numpy().astype(np.float64), g.float().cpu().numpy()
+
+
+def check_against_oracle(Fn, po, z, t, p, kind, dev, tol=TOL, check_sums=True):
+    """z,t: CPU fp32 tensors.  Oracle in fp64 on the same fp32 values is the ground truth."""
+    x = z.to(dev).contiguous()
+    tt = t.to(dev).contiguous()
+    sums, rep, g = gpu_loss_and_grad(Fn, x, tt, lp(Fn, p), kind)
+    z64, t64 = z.numpy().astype(np.float64), t.numpy().astype(np.float64)
+    osums = po.sums(z64, t64, p, kind)
+    ocomp = po.finalize(osums, int(osums[7]), p)
+    og = po.backward(z64, t64, p, osums, int(osums[7]), kind)
+    if check_sums:
+        for k in range(6):
+            assert rel_scalar(sums[k], osums[k]) < tol, f"sum[{k}] {sums[k]} vs {osums[k]}"
+        assert sums[7] == osums[7]
+    for k in range(5):
+        assert rel_scalar(rep[k], ocomp[k]) < tol, f"component {k}: {rep[k]} vs {ocomp[k]}"
+    assert rel_max(g, og) < tol, f"grad max-norm rel {rel_max(g, og)}"
+    assert rel_l2(g, og) < tol, f"grad L2 rel {rel_l2(g, og)}"
+    return sums, rep, g
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors produced by the real reference
+# ------------------------------------------------------------------------------------------------
+def test_golden_reference_cases(golden, Fn, po, dev):
+    data, meta = golden
+    for c in meta["cases"]:
+        n, kind = c["name"], KIND_NAME[c["activation"]]
+        p = lp(Fn, po.Params(**c["params"]))
+        z = torch.from_numpy(data[f"{n}.z"]).to(dev)
+        t = torch.from_numpy(data[f"{n}.t"]).to(dev)
+        # (1) logits entry vs the reference's fp64 evaluation (ground truth) and fp32 evaluation
+        _, rep, g = gpu_loss_and_grad(Fn, z, t, p, kind)
+        floor_g = rel_max(data[f"{n}.f32.dz"], data[f"{n}.f64.dz"])
+        floor_l = rel_scalar(data[f"{n}.f32.loss"], data[f"{n}.f64.loss"])
+        if n != "saturated":
+            # never demand more than the reference's own fp32-vs-fp64 agreement (tanh head: 2.7e-5)
+            assert rel_scalar(rep[0], data[f"{n}.f64.loss"]) < max(TOL, 4 * floor_l), n
+            assert rel_max(g, data[f"{n}.f64.dz"]) < max(TOL, 4 * floor_g), n
+            assert rel_scalar(rep[0], data[f"{n}.f32.loss"]) < max(TOL, 4 * floor_l), n
+            assert rel_max(g, data[f"{n}.f32.dz"]) < max(TOL, 4 * floor_g), n
+        # (2) probability entry on bit-identical fp32 probabilities (what src/train.py:117 passes)
+        act = torch.sigmoid if c["activation"] == "sigmoid" else (lambda v: (torch.tanh(v) + 1.0) / 2.0)
+        u = act(torch.from_numpy(data[f"{n}.z"])).to(dev)
+        _, rep_p, g_p = gpu_loss_and_grad(Fn, u, t, p, Fn.X_PROB)
+        assert rel_scalar(rep_p[0], data[f"{n}.f64.loss_p"]) < TOL, n
+        assert rel_max(g_p, data[f"{n}.f64.du"]) < TOL, n
+        assert rel_l2(g_p, data[f"{n}.f64.du"]) < TOL, n
+        assert rel_max(g_p, data[f"{n}.f32.du"]) < TOL, n
+        for k in range(4):
+            assert rel_scalar(rep_p[1 + k], data[f"{n}.f64.comps_p"][k]) < TOL, (n, k)
+
+
+def test_golden_saturated_semantics(golden, Fn, po, dev):
+    """u == 0 / u == 1 exactly: log clamp at -100, 1e-12 clamp in the BCE gradient, zero gradient
+    through the saturated sigmoid."""
+    data, meta = golden
+    c = next(c for c in meta["cases"] if c["name"] == "saturated")
+    p = lp(Fn, po.Params(**c["params"]))
+    z_np = data["saturated.z"]
+    z, t = torch.from_numpy(z_np).to(dev), torch.from_numpy(data["saturated.t"]).to(dev)
+    _, rep, g = gpu_loss_and_grad(Fn, z, t, p, Fn.X_LOGITS_SIGMOID)
+    ref = data["saturated.f32.dz"]
+    hard = np.abs(z_np) >= 30
+    assert hard.sum() >= 20
+    assert np.all(g[hard] == 0.0) and np.all(ref[hard] == 0.0)
+    soft_px = np.abs(z_np) < 12
+    assert rel_max(g[soft_px], ref[soft_px]) < TOL
+    assert rel_scalar(rep[0], data["saturated.f32.loss"]) < 1e-4  # +-17 logits sit on the fp32 rounding edge of u
+
+
+def test_known_answer_stencils(golden, dev):
+    from physics_informed_image_segmentation_b200 import PDERegularization
+
+    data, _ = golden
+    reg = PDERegularization(1.0, 0.5).to(dev)
+    u = torch.from_numpy(data["ka_u"]).to(dev)
+    assert np.array_equal(reg.compute_laplacian(u).cpu().numpy(), data["ka_lap"])
+    assert np.array_equal(reg.compute_gradient_magnitude(u).cpu().numpy(), data["ka_gms"])
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle on seeded inputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("gen", [iid_inputs, blob_inputs])
+@pytest.mark.parametrize("shape", [(8, 256, 256), (32, 512, 512)])  # BASELINE configs 1 and 2
+def test_stage2_configs_vs_oracle(Fn, po, dev, gen, shape):
+    z, t = gen(*shape, seed=1234)
+    check_against_oracle(Fn, po, z, t, po.STAGE2, Fn.X_LOGITS_SIGMOID, dev)
+
+
+@pytest.mark.parametrize("shape", [
+    (1, 2, 2), (2, 3, 5), (1, 127, 129), (1, 255, 257), (1, 2, 130), (1, 130, 2), (3, 4, 4), (2, 8, 8),
+    (1, 16, 116), (1, 16, 120), (2, 9, 124), (1, 33, 240), (1, 12, 244), (1, 20, 360), (1, 7, 1000), (2, 70, 1024),
+    (1, 1030, 8), (5, 17, 36),
+])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_edge_shapes(Fn, po, dev, shape, kind):
+    """odd sizes (scalar path), strip boundaries of the 120-column tiling (116/120/124/240/244/360),
+    single-row segments, tall and wide extremes"""
+    z, t = iid_inputs(*shape, seed=sum(shape))
+    x = torch.sigmoid(z) if kind == 0 else z
+    check_against_oracle(Fn, po, x, t, po.STAGE2, kind, dev)
+
+
+def test_unaligned_base_pointer(Fn, po, dev):
+    """W % 4 == 0 but the base pointer is only 4-byte aligned -> scalar path must be taken"""
+    z, t = iid_inputs(2, 12, 64, seed=5)
+    buf = torch.empty(z.numel() + 1, device=dev)
+    x = buf[1:].view(z.shape)
+    x.copy_(z)
+    tt = t.to(dev)
+    p = lp(Fn, po.STAGE2)
+    sums, rep, g = gpu_loss_and_grad(Fn, x, tt, p, 1)
+    assert Fn.launch_info().fwd_aligned == 0 and Fn.launch_info().bwd_aligned == 0
+    sums2, rep2, g2 = gpu_loss_and_grad(Fn, z.to(dev), tt, p, 1)
+    assert Fn.launch_info().fwd_aligned == 1
+    assert rel_max(g, g2) < 1e-6 and rel_scalar(rep[0], rep2[0]) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["t0", "t1", "u_const", "soft_t"])
+def test_degenerate_maps(Fn, po, dev, case):
+    z, t = iid_inputs(2, 24, 40, seed=11)
+    if case == "t0":
+        t = torch.zeros_like(t)
+    elif case == "t1":
+        t = torch.ones_like(t)
+    elif case == "u_const":
+        z = torch.full_like(z, 0.3)
+    else:
+        t = torch.rand(t.shape, generator=torch.Generator().manual_seed(3))
+    check_against_oracle(Fn, po, z, t, po.STAGE2, 1, dev, check_sums=(case != "u_const"))
+
+
+@pytest.mark.parametrize("weights", [
+    dict(pde_weight=0.0, phase_field_weight=0.0), dict(pde_weight=1e-3, phase_field_weight=0.0),
+    dict(pde_weight=0.0, phase_field_weight=1e-2), dict(dice_weight=0.0, bce_weight=0.0, pde_weight=1.0, phase_field_weight=1.0),
+    dict(dice_weight=1.0, bce_weight=0.0), dict(dice_weight=0.0, bce_weight=1.0),
+    dict(diffusion_coeff=100.0, pde_weight=1e-3), dict(diffusion_coeff=0.5, pde_weight=1e-3),
+    dict(epsilon=0.001), dict(epsilon=0.2), dict(reaction_threshold=0.2), dict(reaction_threshold=0.8),
+])
+def test_weight_gates_and_sweeps(Fn, po, dev, weights):
+    """the `> 0` gates of src/loss.py:150,:155 and the S1/S2/S3 sweep ranges of run_ablation.py"""
+    import dataclasses
+
+    p = dataclasses.replace(po.STAGE2, **weights)
+    z, t = blob_inputs(3, 48, 64, seed=21)
+    check_against_oracle(Fn, po, z, t, p, 1, dev)
+
+
+def test_tanh_head(Fn, po, dev):
+    z, t = iid_inputs(2, 40, 48, seed=8)
+    z = 0.5 * z  # keep 1 - tanh^2 well conditioned so the fp64 oracle is a fair reference
+    check_against_oracle(Fn, po, z, t, po.STAGE2, 2, dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# reduced-precision storage
+# ------------------------------------------------------------------------------------------------
+def test_bf16_inputs(Fn, po, dev):
+    z, t = blob_inputs(4, 128, 128, seed=2)
+    zb = z.bfloat16()
+    x, tt = zb.to(dev), t.bfloat16().to(dev)
+    sums, rep, g = gpu_loss_and_grad(Fn, x, tt, lp(Fn, po.STAGE2), 1)
+    z64, t64 = zb.float().numpy().astype(np.float64), t.numpy().astype(np.float64)
+    comps, og = po.loss_and_grad(z64, t64, po.STAGE2, 1)
+    assert rel_scalar(rep[0], comps[0]) < 1e-2
+    for k in range(5):
+        assert rel_scalar(rep[k], comps[k]) < 1e-2
+    assert rel_max(g, og) < 1e-2 and rel_l2(g, og) < 1e-2
+    # loss math is fp32 inside: only the gradient's bf16 store rounds
+    assert rel_scalar(rep[0], comps[0]) < 1e-5
+
+
+def test_u8_targets(Fn, po, dev):
+    z, t = iid_inputs(3, 64, 72, seed=4)
+    p = lp(Fn, po.STAGE2)
+    _, rep_f, g_f = gpu_loss_and_grad(Fn, z.to(dev), t.to(dev), p, 1)
+    _, rep_u, g_u = gpu_loss_and_grad(Fn, z.to(dev), t.to(torch.uint8).to(dev), p, 1)
+    _, rep_b, g_b = gpu_loss_and_grad(Fn, z.to(dev), t.bool().to(dev), p, 1)
+    assert np.array_equal(rep_f, rep_u) and np.array_equal(g_f, g_u)
+    assert np.array_equal(rep_f, rep_b) and np.array_equal(g_f, g_b)
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE's full sizes
+# ------------------------------------------------------------------------------------------------
+def test_full_size_shard_additivity_and_determinism(Fn, po, dev):
+    """64 x 1024 x 1024 (north-star shape): (a) running twice is bit-identical, (b) per-shard sums add up
+    to the whole-batch sums, (c) per-shard backward with the global sums is bit-identical to the
+    whole-batch backward -- the data-parallel identity of SURVEY.md 8e, (d) 16 images cross-checked
+    against the oracle."""
+    B, H, W = 64, 1024, 1024
+    g = torch.Generator(device=dev).manual_seed(77)
+    z = 2.0 * torch.randn(B, 1, H, W, device=dev, generator=g)
+    t = (torch.rand(B, 1, H, W, device=dev, generator=g) > 0.5).float()
+    p = lp(Fn, po.STAGE2)
+    s1, r1 = Fn.forward_sums(z, t, p, 1)
+    s2, r2 = Fn.forward_sums(z, t, p, 1)
+    assert torch.equal(s1, s2) and torch.equal(r1, r2)
+    parts = [Fn.forward_sums(z[a:b], t[a:b], p, 1, finalize=False)[0] for a, b in ((0, 8), (8, 40), (40, 64))]
+    tot = parts[0] + parts[1] + parts[2]
+    assert torch.allclose(tot[:6], s1[:6], rtol=1e-12, atol=0) and tot[7] == s1[7] == B * H * W
+    g_full = Fn.backward_grad(z, t, p, 1, s1, z.numel())
+    for a, b in ((0, 8), (8, 40), (40, 64)):
+        g_part = Fn.backward_grad(z[a:b], t[a:b], p, 1, s1, z.numel())
+        assert torch.equal(g_part, g_full[a:b])
+    # loss is linear in its weights: total == sum of weighted components
+    rep = r1.double().cpu().numpy()
+    pp = po.STAGE2
+    lin = pp.dice_weight * rep[1] + pp.bce_weight * rep[2] + pp.pde_weight * rep[3] + pp.phase_field_weight * rep[4]
+    assert rel_scalar(rep[0], lin) < 1e-6
+    # oracle cross-check on a 16-image slice with the GLOBAL sums
+    sl = slice(24, 40)
+    zs, ts = z[sl].cpu().numpy().astype(np.float64), t[sl].cpu().numpy().astype(np.float64)
+    og = po.backward(zs, ts, po.STAGE2, s1.cpu().numpy(), z.numel(), 1)
+    assert rel_max(g_full[sl].cpu().numpy(), og) < TOL
+    osums = po.sums(zs, ts, po.STAGE2, 1)
+    gs, _ = Fn.forward_sums(z[sl], t[sl], p, 1, finalize=False)
+    for k in range(6):
+        assert rel_scalar(gs[k].item(), osums[k]) < TOL
+
+
+def test_forced_segment_lengths_agree(Fn, po, dev):
+    """the tiling is an implementation detail: every rows-per-segment choice gives the same answer"""
+    from physics_informed_image_segmentation_b200 import _lib
+
+    z, t = blob_inputs(2, 100, 256, seed=6)
+    x, tt, p = z.to(dev), t.to(dev), lp(Fn, po.STAGE2)
+    base = None
+    try:
+        for rps in (0, 1, 2, 3, 7, 33, 100, 1000):
+            _lib.lib().pil_set_tuning(rps, rps)
+            sums, rep, g = gpu_loss_and_grad(Fn, x, tt, p, 1)
+            if base is None:
+                base = (sums, g)
+            else:
+                assert np.allclose(sums[:6], base[0][:6], rtol=1e-6, atol=0)
+                assert np.array_equal(g, base[1])
+    finally:
+        _lib.lib().pil_set_tuning(0, 0)
