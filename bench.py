@@ -235,7 +235,8 @@ def run_ours(args):
         dist.barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
-    launches = Fn.launch_info().kernels_launched - k0
+    info = Fn.launch_info()
+    launches = info.kernels_launched - k0
 
     total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
     fwd_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
@@ -282,7 +283,6 @@ def run_ours(args):
         ach_b = bpp_b * n_local / (bwd_med * 1e-3) / 1e9
         ach_f = bpp_f * n_local / (fwd_med * 1e-3) / 1e9
         ach_step = (bpp_f + bpp_b) * n_local * K / (total_ms * 1e-3) / 1e9
-        info = Fn.launch_info()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -55,8 +55,10 @@ class PDERegularization(nn.Module):
 
     # -- scalar losses (fused kernels) ------------------------------------------------------------
     def _params(self, **kw) -> LossParams:
-        return LossParams(dice_weight=0.0, bce_weight=0.0, pde_weight=0.0, phase_field_weight=0.0,
-                          diffusion_coeff=self.diffusion_coeff, reaction_threshold=self.reaction_threshold, **kw)
+        base = dict(dice_weight=0.0, bce_weight=0.0, pde_weight=0.0, phase_field_weight=0.0,
+                    diffusion_coeff=self.diffusion_coeff, reaction_threshold=self.reaction_threshold)
+        base.update(kw)
+        return LossParams(**base)
 
     def compute_loss(self, u: torch.Tensor) -> torch.Tensor:
         """mean(r^2); reference src/pde.py:124-145."""

@@ -1,0 +1,53 @@
+"""Run a few fwd+bwd steps of the Stage II loss on resident tensors (for ncu / quick timing).
+
+    python tools/prof_step.py [--workload cfg3] [--steps 3] [--dtype f32] [--rps-fwd N --rps-bwd N]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import physics_informed_image_segmentation_b200 as P  # noqa: E402
+from physics_informed_image_segmentation_b200 import _lib, functional as Fn  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="cfg3")
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--dtype", default="f32")
+ap.add_argument("--rps-fwd", type=int, default=0)
+ap.add_argument("--rps-bwd", type=int, default=0)
+ap.add_argument("--kind", type=int, default=1)
+a = ap.parse_args()
+B, H, W, name = bench.WORKLOADS[a.workload]
+dev = torch.device("cuda:0")
+dt = torch.float32 if a.dtype == "f32" else torch.bfloat16
+z, t = bench.synth(B, H, W, 1234, dev, dt)
+if a.kind == 0:
+    z = torch.sigmoid(z.float()).to(dt)
+g = torch.empty_like(z)
+p = P.LossParams(**bench.STAGE2)
+sums = torch.empty(8, dtype=torch.float64, device=dev)
+rep = torch.empty(8, dtype=torch.float32, device=dev)
+_lib.lib().pil_set_tuning(a.rps_fwd, a.rps_bwd)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+fm, bm = [], []
+for k in range(a.steps + 3):
+    ev[0].record()
+    Fn.forward_sums(z, t, p, a.kind, sums=sums, report=rep)
+    ev[1].record()
+    Fn.backward_grad(z, t, p, a.kind, sums, z.numel(), out=g)
+    ev[2].record()
+    torch.cuda.synchronize()
+    if k >= 3:
+        fm.append(ev[0].elapsed_time(ev[1]))
+        bm.append(ev[1].elapsed_time(ev[2]))
+info = Fn.launch_info()
+n = z.numel()
+esz = z.element_size()
+f, b = min(fm), min(bm)
+print(f"{name} {a.dtype} kind={a.kind} rps=({info.fwd_rows_per_segment},{info.bwd_rows_per_segment}) blocks=({info.fwd_blocks},{info.bwd_blocks}) "
+      f"fwd {f*1e3:.1f} us {2*esz*n/f/1e6:.0f} GB/s | bwd {b*1e3:.1f} us {3*esz*n/b/1e6:.0f} GB/s | "
+      f"step {n/(f+b)/1e6:.1f} Gpx/s {5*esz*n/(f+b)/1e6:.0f} GB/s loss {rep[0].item():.6f}")
