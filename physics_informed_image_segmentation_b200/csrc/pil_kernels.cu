@@ -33,8 +33,8 @@ constexpr int kOutLanes = 30;               // lanes of a warp that own output c
 constexpr int kStripCols = kOutLanes * kVec;  // 120 output columns per warp
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kFwdMinBlocks = 6;  // 24 warps / SM, <= 85 registers
-constexpr int kBwdMinBlocks = 5;  // 20 warps / SM, <= 102 registers
+constexpr int kFwdMinBlocks = 7;  // 32 warps / SM, <= 64 registers
+constexpr int kBwdMinBlocks = 5;  // 24 warps / SM, <= 85 registers
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kLogClampLog2 = -100.0f * kLog2e;  // nn.BCELoss clamps ln() at -100
@@ -145,6 +145,72 @@ __device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16* p, float v) {
     *p = __float2bfloat16_rn(v);
 }
 
+// ------------------------------------------------------------------------------------------------
+// cp.async stage ring (ALIGNED path): every lane copies its own 16-byte (4-column) piece of the rows
+// it will need kStages-1 iterations ahead into a private shared-memory slot (LDGSTS, no registers
+// held while the load is in flight) and reads it back with one LDS when the row is consumed.  A lane
+// only ever reads what it copied itself, so cp.async.wait_group is the only synchronisation needed.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStages = 6;                       // == unroll factor of the steady-state loops
+constexpr int kStageBytes = 2 * 32 * 16;         // one map row piece + one target row piece per lane
+constexpr int kSmemPerWarp = kStages * kStageBytes;
+constexpr int kSmemPerBlock = kWarpsPerBlock * kSmemPerWarp;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst_shared, const void* src) {
+    if constexpr (BYTES == 16) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_shared), "l"(src), "n"(BYTES) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ float4 lds4(const unsigned char* p);
+template <>
+__device__ __forceinline__ float4 lds4<float>(const unsigned char* p) {
+    return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 lds4<__nv_bfloat16>(const unsigned char* p) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    float4 r;
+    r.x = __uint_as_float(raw.x << 16);
+    r.y = __uint_as_float(raw.x & 0xffff0000u);
+    r.z = __uint_as_float(raw.y << 16);
+    r.w = __uint_as_float(raw.y & 0xffff0000u);
+    return r;
+}
+template <>
+__device__ __forceinline__ float4 lds4<uint8_t>(const unsigned char* p) {
+    const uint32_t raw = *reinterpret_cast<const uint32_t*>(p);
+    return make_float4((float)(raw & 0xff), (float)((raw >> 8) & 0xff), (float)((raw >> 16) & 0xff),
+                       (float)(raw >> 24));
+}
+
+template <typename XT, typename TT>
+struct StageRing {
+    unsigned char* my;   // generic pointer to this lane's slot of stage 0 (map piece); target piece at +512
+    uint32_t my_s;       // same, shared-space address for cp.async
+    __device__ __forceinline__ void init(unsigned char* smem, int warp, int lane) {
+        my = smem + warp * kSmemPerWarp + lane * 16;
+        my_s = (uint32_t)__cvta_generic_to_shared(my);
+    }
+    __device__ __forceinline__ void issue_x(int stage, const XT* src) const {
+        cp_async<4 * (int)sizeof(XT)>(my_s + stage * kStageBytes, src);
+    }
+    __device__ __forceinline__ void issue_t(int stage, const TT* src) const {
+        cp_async<4 * (int)sizeof(TT)>(my_s + stage * kStageBytes + 512, src);
+    }
+    __device__ __forceinline__ float4 read_x(int stage) const { return lds4<XT>(my + stage * kStageBytes); }
+    __device__ __forceinline__ float4 read_t(int stage) const { return lds4<TT>(my + stage * kStageBytes + 512); }
+};
+
 // How one thread reads its 4 columns of a row.  ALIGNED (W % 4 == 0, 16-byte aligned bases): every
 // lane issues one 128-bit load at its column clamped into the image, so the load is branch-free;
 // the two halo lanes that hang over the image edge then move the mirrored column into the slot
@@ -167,14 +233,21 @@ struct Cols {
             for (int p = 0; p < 4; ++p) idx[p] = mirror_clamp(c0 + p, W);
         }
     }
-    // `row` already points at this thread's (clamped) column for ALIGNED, at column 0 otherwise
+    // `row` already points at this thread's (clamped) column for ALIGNED, at column 0 otherwise.
+    // The halo fix-up is a separate step applied when the row is CONSUMED, not when it is fetched:
+    // touching the loaded registers right after the load would stall the warp on the load and
+    // defeat the two-row prefetch (measured: 25% of all stall samples sat on those two selects).
+    __device__ __forceinline__ float4 fix(float4 r) const {
+        if constexpr (ALIGNED) {
+            if (mode == 1) r.w = r.y;
+            if (mode == 2) r.x = r.z;
+        }
+        return r;
+    }
     template <typename T>
     __device__ __forceinline__ float4 load(const T* row) const {
         if constexpr (ALIGNED) {
-            float4 r = ld4<T>(row);
-            if (mode == 1) r.w = r.y;
-            if (mode == 2) r.x = r.z;
-            return r;
+            return ld4<T>(row);
         } else {
             return make_float4(ld1<T>(row + idx[0]), ld1<T>(row + idx[1]), ld1<T>(row + idx[2]),
                                ld1<T>(row + idx[3]));
@@ -195,9 +268,28 @@ template <bool V>
 struct BoolC {
     static constexpr bool value = V;
 };
+// Packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot does two pixels.  Both
+// kernels are issue-limited in scalar form (ncu: ~60% issue-active with the FMA pipe at 40-50%), so
+// every element-wise operation of the ALIGNED path works on (slot0,slot1) / (slot2,slot3) pairs.
+// Scalar constants are broadcast by the instruction itself (R.F32 operand form), no register pairs.
+using f2 = float2;
+__device__ __forceinline__ f2 bc(float s) { return make_float2(s, s); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+
 template <int KIND>
 __device__ __forceinline__ float4 act4(float4 v) {
-    return make_float4(activate<KIND>(v.x), activate<KIND>(v.y), activate<KIND>(v.z), activate<KIND>(v.w));
+    if constexpr (KIND == PIL_X_PROB) {
+        return v;
+    } else {
+        const float s = (KIND == PIL_X_LOGITS_TANH) ? -2.0f * kLog2e : -kLog2e;
+        const f2 a = mul2(make_float2(v.x, v.y), bc(s)), b = mul2(make_float2(v.z, v.w), bc(s));
+        const f2 da = add2(make_float2(ex2_approx(a.x), ex2_approx(a.y)), bc(1.0f));
+        const f2 db = add2(make_float2(ex2_approx(b.x), ex2_approx(b.y)), bc(1.0f));
+        return make_float4(rcp_approx(da.x), rcp_approx(da.y), rcp_approx(db.x), rcp_approx(db.y));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -264,6 +356,84 @@ struct FwdRow {
     float D, a;
     float m[4];  // !ALIGNED: 1 for slots that are real output pixels of this thread
 
+    // ALIGNED: accumulators are kept per slot parity (a0 = even slots, a1 = odd slots) as pairs
+    f2 pa[7];  // 0 I, 1 P, 2 T, 3 bce(log2 units), 4 r^2, 5 dx^2+dy^2, 6 (uv)^2
+    __device__ __forceinline__ void init_packed() {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) pa[k] = make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ void fold_packed() {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc[k] = pa[k].x + pa[k].y;
+    }
+    // ---- packed forward, split in two so that the BCE logarithms can reuse the sigmoid's internals ----
+    // point2(): activation + every per-pixel term of a pixel pair (I, P, T, BCE, double well).
+    //   logits kinds: den = 1 + 2^xs (xs = -z*log2e), u = 1/den, and with ONE more MUFU, L = lg2(den):
+    //       lg2(u)   = -L
+    //       lg2(1-u) = xs - L        (1-u = 2^xs / den)
+    //   i.e. 3 MUFU per pixel instead of 4 (the forward kernel is bound by the XU pipe: ncu 71% with
+    //   mio/math-pipe throttle as the top stalls).  The reference evaluates log(1 - fl(u)); the two agree
+    //   to the reference's own fp32 rounding of u, except where fl(u) == 1 exactly: there the reference's
+    //   log(0) is clamped to -100 (nn.BCELoss), which is reproduced by the v == 0 select below.
+    //   probability kind: u is given, both logarithms are taken directly (2 MUFU).
+    __device__ __forceinline__ f2 point2(f2 x, f2 t, bool count) {
+        f2 u, lu, lv, v;
+        if constexpr (KIND == PIL_X_PROB) {
+            u = x;
+            v = sub2(bc(1.0f), u);
+            lu = make_float2(fmaxf(lg2_approx(u.x), kLogClampLog2), fmaxf(lg2_approx(u.y), kLogClampLog2));
+            lv = make_float2(fmaxf(lg2_approx(v.x), kLogClampLog2), fmaxf(lg2_approx(v.y), kLogClampLog2));
+        } else {
+            const float sc = (KIND == PIL_X_LOGITS_TANH) ? -2.0f * kLog2e : -kLog2e;
+            const f2 xs = mul2(x, bc(sc));
+            const f2 den = add2(make_float2(ex2_approx(xs.x), ex2_approx(xs.y)), bc(1.0f));
+            u = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+            const f2 L = make_float2(lg2_approx(den.x), lg2_approx(den.y));
+            v = sub2(bc(1.0f), u);
+            lu = make_float2(fmaxf(-L.x, kLogClampLog2), fmaxf(-L.y, kLogClampLog2));
+            // u*(1-u) == 0 exactly <=> fl(u) is 0 (2^xs overflowed, L = inf) or 1 (2^xs absorbed):
+            // there lg2(1-u) is 0 resp. the clamp -- i.e. clamp*u -- instead of xs - L.
+            const f2 d = sub2(xs, L), sp = mul2(bc(kLogClampLog2), u), uvz = mul2(u, v);
+            lv = make_float2(uvz.x == 0.0f ? sp.x : d.x, uvz.y == 0.0f ? sp.y : d.y);
+        }
+        if (count) {
+            const f2 uv = mul2(u, v);
+            pa[0] = fma2(u, t, pa[0]);
+            pa[1] = add2(pa[1], u);
+            pa[2] = add2(pa[2], t);
+            pa[3] = add2(pa[3], fma2(t, sub2(lu, lv), lv));  // t*lu + (1-t)*lv
+            pa[6] = fma2(uv, uv, pa[6]);
+            if constexpr (KIND == PIL_X_PROB) {
+                acc[7] += (u.x >= 0.0f && u.x <= 1.0f) ? 0.0f : 1.0f;
+                acc[7] += (u.y >= 0.0f && u.y <= 1.0f) ? 0.0f : 1.0f;
+            }
+        }
+        return u;
+    }
+    __device__ __forceinline__ float4 point4(const float4& x, const float4& t, bool count) {
+        const f2 a2 = point2(make_float2(x.x, x.y), make_float2(t.x, t.y), count);
+        const f2 b2 = point2(make_float2(x.z, x.w), make_float2(t.z, t.w), count);
+        return make_float4(a2.x, a2.y, b2.x, b2.y);
+    }
+    // stencil2(): residual and gradient-energy terms of a pixel pair of the centre row.
+    //   r = D*(s4 - 4u) + u(1-u)(u-a) as a polynomial in u: u*(u*((1+a) - u) - a - 4D) + D*s4
+    float a1, c0;  // 1+a, -a-4D
+    __device__ __forceinline__ void stencil2(f2 u, f2 lf, f2 rt, f2 m, f2 p) {
+        const f2 s4 = add2(add2(lf, rt), add2(m, p));                                       // src/pde.py:73-77
+        const f2 r = fma2(u, fma2(u, sub2(bc(a1), u), bc(c0)), mul2(bc(D), s4));            // src/pde.py:99,:120
+        const f2 dx = sub2(rt, lf), dy = sub2(p, m);                                        // 2*gx, 2*gy (src/pde.py:172-173)
+        pa[4] = fma2(r, r, pa[4]);
+        pa[5] = fma2(dx, dx, pa[5]);
+        pa[5] = fma2(dy, dy, pa[5]);
+    }
+    __device__ __forceinline__ void stencil4(const float4& um, const float4& uc, const float4& up) {
+        const float L = __shfl_up_sync(0xffffffffu, uc.w, 1);
+        const float R = __shfl_down_sync(0xffffffffu, uc.x, 1);
+        const f2 A = make_float2(L, uc.x), B = make_float2(uc.y, uc.z), C = make_float2(uc.w, R);
+        stencil2(make_float2(uc.x, uc.y), A, B, make_float2(um.x, um.y), make_float2(up.x, up.y));
+        stencil2(make_float2(uc.z, uc.w), B, C, make_float2(um.z, um.w), make_float2(up.z, up.w));
+    }
+
     __device__ __forceinline__ void row(const float4& um, const float4& uc, const float4& up, const float4& tt) {
         const float L = __shfl_up_sync(0xffffffffu, uc.w, 1);
         const float R = __shfl_down_sync(0xffffffffu, uc.x, 1);
@@ -316,8 +486,11 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
     FwdRow<KIND, ALIGNED> fr;
 #pragma unroll
     for (int k = 0; k < 8; ++k) fr.acc[k] = 0.f;
+    fr.init_packed();
     fr.D = A.D;
     fr.a = A.a;
+    fr.a1 = 1.0f + A.a;
+    fr.c0 = -A.a - 4.0f * A.D;
 
     if (task < g.tasks) {
         const int strip = (int)(task % g.strips);
@@ -345,40 +518,121 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
         auto xrow = [&](int k) -> const XT* { return xb + (unsigned)(mirror_clamp(k, H) * W); };
         auto trow = [&](int k) -> const TT* { return tb + (unsigned)(min(k, H - 1) * W); };
 
-        // prologue: rows r0-1, r0 become u; rows r0+1, r0+2 and targets r0, r0+1 are in flight
-        const float4 x0 = cx.template load<XT>(xrow(r0 - 1)), x1 = cx.template load<XT>(xrow(r0));
-        float4 xq0 = cx.template load<XT>(xrow(r0 + 1));
-        float4 xq1 = cx.template load<XT>(xrow(min(r0 + 2, r1)));
-        float4 tq0 = cx.template load_plain<TT>(trow(r0));
-        float4 tq1 = cx.template load_plain<TT>(trow(r0 + 1));
-        float4 um = act4<KIND>(x0), uc = act4<KIND>(x1);
-        const XT* px = xb + (unsigned)((r0 + 3) * W);  // next map row to fetch (row i+3)
-        const TT* pt = tb + (unsigned)((r0 + 2) * W);  // next target row to fetch (row i+2)
+        if constexpr (ALIGNED) {
+            // ---- staged path: iteration i consumes stage (i-r0)%6 = {map row i+1, target row i+1} ----
+            // It activates row i+1 and adds that row's per-pixel terms (if the segment owns it), then adds
+            // the stencil terms of row i, whose three u rows are now all in registers.
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            StageRing<XT, TT> ring;
+            ring.init(smem_raw, warp, lane);
+            const XT* px = xb + (unsigned)((r0 + 1) * W);  // map row of the next iteration to be issued
+            const TT* pt = tb + (unsigned)((r0 + 1) * W);  // target row of the next iteration to be issued
+            // issue(j): the copies iteration j will consume; CHECK handles the segment/image end
+            auto issue = [&](int j, int stage, auto check) {
+                constexpr bool CHECK = decltype(check)::value;
+                if constexpr (CHECK) {
+                    if (j < r1) ring.issue_x(stage, (j + 1 == H) ? px - 2 * W : px);  // row H := row H-2 (mirror)
+                    if (j + 1 < r1) ring.issue_t(stage, pt);
+                } else {
+                    ring.issue_x(stage, px);
+                    ring.issue_t(stage, pt);
+                }
+                px += W;
+                pt += W;
+                cp_async_commit();
+            };
+            const float4 x0 = cx.template load<XT>(xrow(r0 - 1)), x1 = cx.template load<XT>(xrow(r0));
+            const float4 t1 = cx.template load_plain<TT>(trow(r0));
+#pragma unroll
+            for (int q = 0; q < kStages - 1; ++q) issue(r0 + q, q, BoolC<true>{});
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 U0 = fr.point4(cx.fix(x0), zero4, false);  // row r0-1: halo row, contributes no pixel terms
+            float4 U1 = fr.point4(cx.fix(x1), t1, true);      // row r0
+            float4 U2;
 
-        // CHECK=false: steady state, every fetched row is inside the segment and the image.
-        auto step = [&](int i, auto check) {
-            constexpr bool CHECK = decltype(check)::value;
-            const float4 xn = xq0, tn = tq0;
-            xq0 = xq1;
-            tq0 = tq1;
-            if constexpr (CHECK) {
-                if (i + 3 <= r1) xq1 = cx.template load<XT>((i + 3 == H) ? px - 2 * W : px);  // row H := row H-2
-                if (i + 2 < r1) tq1 = cx.template load_plain<TT>(pt);
-            } else {
-                xq1 = cx.template load<XT>(px);
-                tq1 = cx.template load_plain<TT>(pt);
+            auto step = [&](int i, int stage, auto check, const float4& um, const float4& uc, float4& up) {
+                constexpr bool CHECK = decltype(check)::value;
+                issue(i + kStages - 1, (stage + kStages - 1) % kStages, check);
+                cp_async_wait<kStages - 1>();
+                const float4 xn = ring.read_x(stage), tn = ring.read_t(stage);
+                up = fr.point4(cx.fix(xn), tn, !CHECK || (i + 1 < r1));
+                fr.stencil4(um, uc, up);
+            };
+            int i = r0;
+            // steady state: the issue of iteration i+5+5 must stay clean -> i + 11 <= r1 - 2
+#pragma unroll 1
+            for (; i + 2 * kStages <= r1 - 1; i += kStages) {
+                step(i + 0, 0, BoolC<false>{}, U0, U1, U2);
+                step(i + 1, 1, BoolC<false>{}, U1, U2, U0);
+                step(i + 2, 2, BoolC<false>{}, U2, U0, U1);
+                step(i + 3, 3, BoolC<false>{}, U0, U1, U2);
+                step(i + 4, 4, BoolC<false>{}, U1, U2, U0);
+                step(i + 5, 5, BoolC<false>{}, U2, U0, U1);
             }
-            px += W;
-            pt += W;
-            const float4 up = act4<KIND>(xn);
-            fr.row(um, uc, up, tn);
-            um = uc;
-            uc = up;
-        };
-        int i = r0;
-#pragma unroll 2
-        for (; i < r1 - 3; ++i) step(i, BoolC<false>{});
-        for (; i < r1; ++i) step(i, BoolC<true>{});
+            int stage = 0;
+#pragma unroll 1
+            for (; i < r1; ++i) {  // segment tail (and short segments): dynamic stage, explicit rotation
+                step(i, stage, BoolC<true>{}, U0, U1, U2);
+                stage = (stage + 1 == kStages) ? 0 : stage + 1;
+                U0 = U1;
+                U1 = U2;
+            }
+            cp_async_wait<0>();
+            fr.fold_packed();
+        } else {
+            // prologue: rows r0-1, r0 become u; rows r0+1, r0+2 and targets r0, r0+1 are in flight.
+            // Two fetch slots (A,B) alternate: iteration i consumes the slot holding map row i+1 / target
+            // row i and immediately refills it with rows i+3 / i+2, so loaded registers are never moved
+            // (a MOV of a loaded register would stall on the load and defeat the prefetch).
+            const float4 x0 = cx.template load<XT>(xrow(r0 - 1)), x1 = cx.template load<XT>(xrow(r0));
+            float4 xA = cx.template load<XT>(xrow(r0 + 1));
+            float4 xB = cx.template load<XT>(xrow(min(r0 + 2, r1)));
+            float4 tA = cx.template load_plain<TT>(trow(r0));
+            float4 tB = cx.template load_plain<TT>(trow(r0 + 1));
+            float4 U0 = act4<KIND>(cx.fix(x0)), U1 = act4<KIND>(cx.fix(x1)), U2;
+            const XT* px = xb + (unsigned)((r0 + 3) * W);  // next map row to fetch (row i+3)
+            const TT* pt = tb + (unsigned)((r0 + 2) * W);  // next target row to fetch (row i+2)
+
+            // CHECK=false: steady state, every fetched row is inside the segment and the image.
+            auto step = [&](int i, auto check, float4& xs, float4& ts, const float4& um, const float4& uc, float4& up) {
+                constexpr bool CHECK = decltype(check)::value;
+                const float4 xn = xs, tn = ts;
+                if constexpr (CHECK) {
+                    if (i + 3 <= r1) xs = cx.template load<XT>((i + 3 == H) ? px - 2 * W : px);  // row H := row H-2
+                    if (i + 2 < r1) ts = cx.template load_plain<TT>(pt);
+                } else {
+                    xs = cx.template load<XT>(px);
+                    ts = cx.template load_plain<TT>(pt);
+                }
+                px += W;
+                pt += W;
+                up = act4<KIND>(cx.fix(xn));
+                fr.row(um, uc, up, tn);
+            };
+            int i = r0;
+#pragma unroll 1
+            for (; i + 6 <= r1 - 3; i += 6) {
+                step(i + 0, BoolC<false>{}, xA, tA, U0, U1, U2);
+                step(i + 1, BoolC<false>{}, xB, tB, U1, U2, U0);
+                step(i + 2, BoolC<false>{}, xA, tA, U2, U0, U1);
+                step(i + 3, BoolC<false>{}, xB, tB, U0, U1, U2);
+                step(i + 4, BoolC<false>{}, xA, tA, U1, U2, U0);
+                step(i + 5, BoolC<false>{}, xB, tB, U2, U0, U1);
+            }
+#pragma unroll 1
+            for (; i < r1; ++i) {  // segment tail (and short segments): same step, explicit rotation
+                step(i, BoolC<true>{}, xA, tA, U0, U1, U2);
+                float4 sw = xA;
+                xA = xB;
+                xB = sw;
+                sw = tA;
+                tA = tB;
+                tB = sw;
+                U0 = U1;
+                U1 = U2;
+            }
+
+        }
 
         if constexpr (ALIGNED) {
             if (!counted) {
@@ -456,11 +710,11 @@ struct BwdCoef {
     float alpha, beta;   // dice: d/du = alpha*t + beta                    (du space)
     float cb;            // bce : cb*(u-t)/max(uv,1e-12)                   (du space)
     float cA;            // rd  : cA * (L^T r)      cA = scale*lrd*2/N*D
-    float cF;            // rd  : cF * f'(u) * r    cF = scale*lrd*2/N
+    float f3, f2, f1;    // rd  : cF * f'(u) = f3 u^2 + f2 u + f1,  cF = scale*lrd*2/N, f' = -3u^2 + 2(1+a)u - a
     float cG;            // pf  : cG * (dx[p-1]-dx[p+1] + dy[i-1]-dy[i+1]),  cG = scale*lpf/N*eps/4
     float cW;            // pf  : cW * uv*(1-2u),   cW = scale*lpf/N*2/eps
-    float D, a;
-    float fa2, fa;       // f'(u) = -3u^2 + fa2*u - fa,  fa2 = 2(1+a)
+    float D;
+    float a1, c0;        // r = u*(u*(a1 - u) + c0) + D*(sum of 4 neighbours),  a1 = 1+a, c0 = -a - 4D
 };
 
 template <int KIND, typename XT, typename TT, bool ALIGNED>
@@ -484,13 +738,14 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         c.cb = (float)(scale * A.p.bce_weight * invN);
         const double crd = use_rd ? scale * A.p.pde_weight * 2.0 * invN : 0.0;
         c.cA = (float)(crd * A.p.diffusion_coeff);
-        c.cF = (float)crd;
+        c.f3 = (float)(-3.0 * crd);
+        c.f2 = (float)(2.0 * (1.0 + A.p.reaction_threshold) * crd);
+        c.f1 = (float)(-A.p.reaction_threshold * crd);
         c.cG = use_pf ? (float)(scale * A.p.phase_field_weight * invN * A.p.epsilon * 0.25) : 0.f;
         c.cW = use_pf ? (float)(scale * A.p.phase_field_weight * invN * 2.0 / A.p.epsilon) : 0.f;
         c.D = (float)A.p.diffusion_coeff;
-        c.a = (float)A.p.reaction_threshold;
-        c.fa2 = 2.0f * (1.0f + c.a);
-        c.fa = c.a;
+        c.a1 = (float)(1.0 + A.p.reaction_threshold);
+        c.c0 = (float)(-A.p.reaction_threshold - 4.0 * A.p.diffusion_coeff);
     }
 
     const int strip = (int)(task % g.strips);
@@ -503,7 +758,6 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
     const int col0 = strip * kStripCols + (lane - 1) * kVec;
     const bool out_lane = (lane >= 1) && (lane <= kOutLanes);
     const bool in_img = col0 >= 0 && col0 < W;  // ALIGNED: whole vector in the image
-    const bool edge_warp = (strip == 0) || (strip == g.strips - 1);
 
     Cols<ALIGNED> cx;
     cx.init(col0, W);
@@ -529,33 +783,27 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
 
     // iteration k forms the residual row k (needs u rows k-1, k, k+1) and emits gradient row k-1.
     // k runs r0-1 .. r1; u rows r0-2 .. r1+1 are read (mirrored at the image edge).
+    // The u rows and the gradient accumulators live in rings of three that are renamed, not moved, in
+    // the 6x unrolled steady state.  Rows are fetched 5 iterations ahead: through the cp.async stage
+    // ring on the ALIGNED path, through two alternating register slots otherwise.
     const int k0 = r0 - 1;
-    float4 ua = act4<KIND>(cx.template load<XT>(xrow(k0 - 1)));  // row k-1
-    float4 ub = act4<KIND>(cx.template load<XT>(xrow(k0)));      // row k
-    float4 xq0 = cx.template load<XT>(xrow(k0 + 1));             // row k+1 (consumed by the first iteration)
-    float4 xq1 = cx.template load<XT>(xrow(k0 + 2));
-    float4 tq0 = cx.template load_plain<TT>(trow(r0));           // consumed when row r0 is emitted (k = r0+1)
-    float4 tq1 = cx.template load_plain<TT>(trow(r0 + 1));
-    const XT* px = xb + (unsigned)((k0 + 3) * W);                // next map row to fetch (row k+3)
-    const TT* pt = tb + (unsigned)((r0 + 2) * W);                // next target row to fetch (row k+1 at k = r0+1)
-    XT* pg = gb + (unsigned)(r0 * W) + (ALIGNED ? col0 : 0);     // next gradient row to store (row k-1)
-    float gm[4] = {0.f, 0.f, 0.f, 0.f}, g0[4] = {0.f, 0.f, 0.f, 0.f}, gp[4];
+    const float4 xa = cx.template load<XT>(xrow(k0 - 1)), xbq = cx.template load<XT>(xrow(k0));
+    XT* pg = gb + (unsigned)(r0 * W) + (ALIGNED ? col0 : 0);  // next gradient row to store (row k-1)
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 U0, U1, U2;                  // u rows k-1, k, k+1 (the step produces k+1)
+    float4 G0 = zero4, G1 = zero4, G2;  // gradient accumulators of rows k-1, k, k+1
 
-    // CHECK=false: steady state -- row k strictly inside the image and the segment, all fetches valid.
-    auto step = [&](int k, auto check) {
+    // compute part of one iteration, given the freshly fetched map row k+1 (xn) and, when a row is
+    // emitted, target row k-1 (tn).  CHECK=false: steady state -- row k strictly inside the image.
+    auto compute_scalar = [&](int k, auto check, const float4& xn, const float4& tn, const float4& ua, const float4& ub,
+                       float4& uc4, float4& gm4, float4& g04, float4& gp4) {
         constexpr bool CHECK = decltype(check)::value;
-        const float4 xn = xq0;
-        xq0 = xq1;
-        if constexpr (CHECK) {
-            if (k + 3 <= min(r1 + 1, H)) xq1 = cx.template load<XT>((k + 3 == H) ? px - 2 * W : px);  // row H := row H-2
-        } else {
-            xq1 = cx.template load<XT>(px);
-        }
-        px += W;
-        const float4 uc4 = act4<KIND>(xn);  // row k+1
-
+        uc4 = act4<KIND>(cx.fix(xn));  // row k+1
         const float va[4] = {ua.x, ua.y, ua.z, ua.w};
         const float vc[4] = {uc4.x, uc4.y, uc4.z, uc4.w};
+        float gm[4] = {gm4.x, gm4.y, gm4.z, gm4.w};
+        float g0[4] = {g04.x, g04.y, g04.z, g04.w};
+        float gp[4];
         if (!CHECK || (k >= 0 && k < H)) {
             const float L = __shfl_up_sync(0xffffffffu, ub.w, 1);
             const float R = __shfl_down_sync(0xffffffffu, ub.x, 1);
@@ -564,13 +812,21 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const float u = e[p + 1];
-                const float uv = u * (1.0f - u);
-                const float lap = (e[p] + e[p + 2]) + (va[p] + vc[p]) - 4.0f * u;
-                r[p] = fmaf(c.D, lap, uv * (u - c.a));
+                const float s4 = (e[p] + e[p + 2]) + (va[p] + vc[p]);
+                // r = D*(s4 - 4u) + u(1-u)(u-a), as a polynomial in u   (src/pde.py:73-77,:99,:120)
+                r[p] = fmaf(u, fmaf(u, c.a1 - u, c.c0), c.D * s4);
                 rc[p] = r[p];
                 dx[p] = e[p + 2] - e[p];
             }
-            if (!ALIGNED || edge_warp) {
+            if constexpr (ALIGNED) {
+                // only slots 0 and 3 can be an image-edge column or feed a neighbour lane; four
+                // unconditional multiplies by per-thread constants (1 everywhere but at the edges)
+                // beat a predicated block, which ptxas expands to 8 issue slots per row in every warp.
+                rc[0] = r[0] * fc[0];
+                rc[3] = r[3] * fc[3];
+                dx[0] *= mc[0];
+                dx[3] *= mc[3];
+            } else {
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     rc[p] *= fc[p];
@@ -588,14 +844,13 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const float u = e[p + 1];
-                const float q = cAr * r[p];
                 const float ey = c.cG * (vc[p] - va[p]);
-                gp[p] = q + ey;   // into row k+1
-                gm[p] += q - ey;  // into row k-1
-                const float fprime = fmaf(u, fmaf(-3.0f, u, c.fa2), -c.fa);
+                gp[p] = fmaf(cAr, r[p], ey);           // into row k+1
+                gm[p] = fmaf(cAr, r[p], gm[p] - ey);   // into row k-1
+                const float fpr = fmaf(u, fmaf(c.f3, u, c.f2), c.f1);  // cF * f'(u)
                 float acc = g0[p];
                 acc = fmaf(c.cA, (re[p] + re[p + 2]) - 4.0f * r[p], acc);
-                acc = fmaf(c.cF * fprime, r[p], acc);
+                acc = fmaf(fpr, r[p], acc);
                 acc = fmaf(c.cG, de[p] - de[p + 2], acc);
                 g0[p] = acc;
             }
@@ -603,17 +858,11 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
 #pragma unroll
             for (int p = 0; p < 4; ++p) gp[p] = 0.f;
         }
+        g04 = make_float4(g0[0], g0[1], g0[2], g0[3]);
+        gp4 = make_float4(gp[0], gp[1], gp[2], gp[3]);
 
         if (!CHECK || k - 1 >= r0) {
             // emit gradient row k-1 : pointwise terms + accumulated stencil terms, then the chain factor
-            const float4 tn = tq0;
-            tq0 = tq1;
-            if constexpr (CHECK) {
-                if (k + 1 < r1) tq1 = cx.template load_plain<TT>(pt);
-            } else {
-                tq1 = cx.template load_plain<TT>(pt);
-            }
-            pt += W;
             const float vt[4] = {tn.x, tn.y, tn.z, tn.w};
             float o[4];
 #pragma unroll
@@ -641,20 +890,190 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
             }
             pg += W;
         }
-        ua = ub;
-        ub = uc4;
+    };
+
+    // Packed (fp32x2) form of the same iteration for the ALIGNED path: identical arithmetic, two
+    // pixels per issue slot.  Pairs are (slot0,slot1) and (slot2,slot3); horizontal neighbours come
+    // from the three shifted pairs A=(L,s0) B=(s1,s2) C=(s3,R).
+    auto compute_packed = [&](int k, auto check, const float4& xn, const float4& tn, const float4& ua, const float4& ub,
+                              float4& uc4, float4& gm4, float4& g04, float4& gp4) {
+        constexpr bool CHECK = decltype(check)::value;
+        uc4 = act4<KIND>(cx.fix(xn));  // row k+1
+        const f2 va[2] = {make_float2(ua.x, ua.y), make_float2(ua.z, ua.w)};
+        const f2 vc[2] = {make_float2(uc4.x, uc4.y), make_float2(uc4.z, uc4.w)};
+        f2 gm[2] = {make_float2(gm4.x, gm4.y), make_float2(gm4.z, gm4.w)};
+        f2 g0[2] = {make_float2(g04.x, g04.y), make_float2(g04.z, g04.w)};
+        f2 gp[2];
+        if (!CHECK || (k >= 0 && k < H)) {
+            const float L = __shfl_up_sync(0xffffffffu, ub.w, 1);
+            const float R = __shfl_down_sync(0xffffffffu, ub.x, 1);
+            const f2 u[2] = {make_float2(ub.x, ub.y), make_float2(ub.z, ub.w)};
+            const f2 eA = make_float2(L, ub.x), eB = make_float2(ub.y, ub.z), eC = make_float2(ub.w, R);
+            const f2 lf[2] = {eA, eB}, rt[2] = {eB, eC};
+            f2 r[2], dx[2];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            gm[p] = g0[p];
-            g0[p] = gp[p];
+            for (int h = 0; h < 2; ++h) {
+                const f2 s4 = add2(add2(lf[h], rt[h]), add2(va[h], vc[h]));
+                // r = D*(s4 - 4u) + u(1-u)(u-a), as a polynomial in u   (src/pde.py:73-77,:99,:120)
+                r[h] = fma2(u[h], fma2(u[h], sub2(bc(c.a1), u[h]), bc(c.c0)), mul2(bc(c.D), s4));
+                dx[h] = sub2(rt[h], lf[h]);
+            }
+            // only slots 0 and 3 can be an image-edge column or feed a neighbour lane
+            const float rc0 = r[0].x * fc[0], rc3 = r[1].y * fc[3];
+            dx[0].x *= mc[0];
+            dx[1].y *= mc[3];
+            const float rL = __shfl_up_sync(0xffffffffu, rc3, 1);
+            const float rR = __shfl_down_sync(0xffffffffu, rc0, 1);
+            const float dL = __shfl_up_sync(0xffffffffu, dx[1].y, 1);
+            const float dR = __shfl_down_sync(0xffffffffu, dx[0].x, 1);
+            const f2 rA = make_float2(rL, rc0), rB = make_float2(r[0].y, r[1].x), rC = make_float2(rc3, rR);
+            const f2 dA = make_float2(dL, dx[0].x), dB = make_float2(dx[0].y, dx[1].x), dC = make_float2(dx[1].y, dR);
+            const f2 rl[2] = {rA, rB}, rr[2] = {rB, rC}, dl[2] = {dA, dB}, dr[2] = {dB, dC};
+            // row factor of the transposed vertical stencil; dy of an edge row is 0 by mirroring
+            const float cAr = (CHECK && (k == 0 || k == H - 1)) ? 2.0f * c.cA : c.cA;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const f2 ey = mul2(bc(c.cG), sub2(vc[h], va[h]));
+                gp[h] = fma2(bc(cAr), r[h], ey);                 // into row k+1
+                gm[h] = fma2(bc(cAr), r[h], sub2(gm[h], ey));    // into row k-1
+                const f2 fpr = fma2(u[h], fma2(bc(c.f3), u[h], bc(c.f2)), bc(c.f1));  // cF * f'(u)
+                f2 acc = g0[h];
+                acc = fma2(bc(c.cA), fma2(bc(-4.0f), r[h], add2(rl[h], rr[h])), acc);
+                acc = fma2(fpr, r[h], acc);
+                acc = fma2(bc(c.cG), sub2(dl[h], dr[h]), acc);
+                g0[h] = acc;
+            }
+        } else {
+            gp[0] = gp[1] = make_float2(0.f, 0.f);
+        }
+        g04 = make_float4(g0[0].x, g0[0].y, g0[1].x, g0[1].y);
+        gp4 = make_float4(gp[0].x, gp[0].y, gp[1].x, gp[1].y);
+
+        if (!CHECK || k - 1 >= r0) {
+            // emit gradient row k-1 : pointwise terms + accumulated stencil terms, then the chain factor
+            const f2 vt[2] = {make_float2(tn.x, tn.y), make_float2(tn.z, tn.w)};
+            f2 o[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const f2 u = va[h], t = vt[h];
+                const f2 v = sub2(bc(1.0f), u);
+                const f2 uv = mul2(u, v);
+                f2 du = add2(gm[h], fma2(bc(c.alpha), t, bc(c.beta)));
+                du = fma2(mul2(bc(c.cW), uv), sub2(v, u), du);
+                const f2 w = mul2(bc(c.cb), sub2(u, t));
+                if constexpr (KIND == PIL_X_PROB) {
+                    const f2 inv = make_float2(rcp_approx(fmaxf(uv.x, 1e-12f)), rcp_approx(fmaxf(uv.y, 1e-12f)));
+                    o[h] = fma2(w, inv, du);
+                } else {
+                    // (u-t)/max(uv,1e-12) * uv  ==  (u-t) * sat(uv*1e12)
+                    const f2 m = make_float2(__saturatef(uv.x * 1e12f), __saturatef(uv.y * 1e12f));
+                    o[h] = fma2(du, uv, mul2(w, m));
+                }
+            }
+            if (store_vec) st4<XT>(pg, make_float4(o[0].x, o[0].y, o[1].x, o[1].y));
+            pg += W;
+        }
+    };
+    auto compute = [&](int k, auto check, const float4& xn, const float4& tn, const float4& ua, const float4& ub,
+                       float4& uc4, float4& gm4, float4& g04, float4& gp4) {
+        if constexpr (ALIGNED) {
+            compute_packed(k, check, xn, tn, ua, ub, uc4, gm4, g04, gp4);
+        } else {
+            compute_scalar(k, check, xn, tn, ua, ub, uc4, gm4, g04, gp4);
         }
     };
 
-    int k = k0;
-    for (; k <= r1 && k <= r0; ++k) step(k, BoolC<true>{});
-#pragma unroll 2
-    for (; k <= r1 - 4; ++k) step(k, BoolC<false>{});
-    for (; k <= r1; ++k) step(k, BoolC<true>{});
+    if constexpr (ALIGNED) {
+        // ---- staged path: iteration k consumes stage (k-k0)%6 = {map row k+1, target row k-1} ----
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        StageRing<XT, TT> ring;
+        ring.init(smem_raw, warp, lane);
+        const XT* px = xb + (long long)(k0 + 1) * W;  // map row of the next iteration to be issued
+        const TT* pt = tb + (long long)(k0 - 1) * W;  // target row of the next iteration to be issued
+        auto issue = [&](int j, int stage, auto check) {
+            constexpr bool CHECK = decltype(check)::value;
+            if constexpr (CHECK) {
+                if (j + 1 <= min(r1 + 1, H)) ring.issue_x(stage, (j + 1 == H) ? px - 2 * W : px);  // row H := row H-2
+                if (j - 1 >= r0 && j - 1 < r1) ring.issue_t(stage, pt);
+            } else {
+                ring.issue_x(stage, px);
+                ring.issue_t(stage, pt);
+            }
+            px += W;
+            pt += W;
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int q = 0; q < kStages - 1; ++q) issue(k0 + q, q, BoolC<true>{});
+        U0 = act4<KIND>(cx.fix(xa));   // row k0-1
+        U1 = act4<KIND>(cx.fix(xbq));  // row k0
+
+        auto step = [&](int k, int stage, auto check, const float4& ua, const float4& ub, float4& uc4, float4& gm4,
+                        float4& g04, float4& gp4) {
+            issue(k + kStages - 1, (stage + kStages - 1) % kStages, check);
+            cp_async_wait<kStages - 1>();
+            const float4 xn = ring.read_x(stage), tn = ring.read_t(stage);
+            compute(k, check, xn, tn, ua, ub, uc4, gm4, g04, gp4);
+        };
+        int k = k0, stage = 0;
+        auto rot_step = [&](int kk) {
+            step(kk, stage, BoolC<true>{}, U0, U1, U2, G0, G1, G2);
+            stage = (stage + 1 == kStages) ? 0 : stage + 1;
+            U0 = U1;
+            U1 = U2;
+            G0 = G1;
+            G1 = G2;
+        };
+        rot_step(k++);  // k = r0-1: forms r[r0-1], emits nothing
+        rot_step(k++);  // k = r0  : forms r[r0],   emits nothing
+        // steady state: compute clean for k in [r0+1, r1-4]; issue (k+5) clean for k+5 <= r1-2
+#pragma unroll 1
+        for (; k + 5 <= r1 - 7; k += kStages) {
+            step(k + 0, 2, BoolC<false>{}, U0, U1, U2, G0, G1, G2);
+            step(k + 1, 3, BoolC<false>{}, U1, U2, U0, G1, G2, G0);
+            step(k + 2, 4, BoolC<false>{}, U2, U0, U1, G2, G0, G1);
+            step(k + 3, 5, BoolC<false>{}, U0, U1, U2, G0, G1, G2);
+            step(k + 4, 0, BoolC<false>{}, U1, U2, U0, G1, G2, G0);
+            step(k + 5, 1, BoolC<false>{}, U2, U0, U1, G2, G0, G1);
+        }
+#pragma unroll 1
+        for (; k <= r1; ++k) rot_step(k);
+        cp_async_wait<0>();
+    } else {
+        // ---- register path (scalar loads): two alternating fetch slots, two rows ahead ----
+        float4 xA = cx.template load<XT>(xrow(k0 + 1));   // row k+1 of the first iteration
+        float4 xB = cx.template load<XT>(xrow(k0 + 2));
+        float4 tA = cx.template load_plain<TT>(trow(r0));  // consumed when row r0 is emitted (k = r0+1)
+        float4 tB = cx.template load_plain<TT>(trow(r0 + 1));
+        U0 = act4<KIND>(cx.fix(xa));
+        U1 = act4<KIND>(cx.fix(xbq));
+        const XT* px = xb + (unsigned)((k0 + 3) * W);  // next map row to fetch (row k+3)
+        const TT* pt = tb + (unsigned)((r0 + 2) * W);  // next target row to fetch
+#pragma unroll 1
+        for (int k = k0; k <= r1; ++k) {
+            const float4 xn = xA, tn = tA;
+            if (k + 3 <= min(r1 + 1, H)) xA = cx.template load<XT>((k + 3 == H) ? px - 2 * W : px);
+            px += W;
+            const bool emits = k - 1 >= r0;
+            if (emits) {
+                if (k + 1 < r1) tA = cx.template load_plain<TT>(pt);
+                pt += W;
+            }
+            compute(k, BoolC<true>{}, xn, tn, U0, U1, U2, G0, G1, G2);
+            float4 sw = xA;
+            xA = xB;
+            xB = sw;
+            if (emits) {
+                sw = tA;
+                tA = tB;
+                tB = sw;
+            }
+            U0 = U1;
+            U1 = U2;
+            G0 = G1;
+            G1 = G2;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -800,10 +1219,16 @@ static bool is_aligned_case(const void* x, const void* t, const void* gptr, int6
 
 template <int KIND, typename XT, typename TT>
 static cudaError_t launch_fwd_a(const FwdArgs& a, bool aligned, int blocks, cudaStream_t s) {
-    if (aligned)
-        pil_fwd_kernel<KIND, XT, TT, true><<<blocks, kThreads, 0, s>>>(a);
-    else
+    if (aligned) {
+        static bool configured = false;  // per template instantiation
+        if (!configured) {
+            cudaFuncSetAttribute(pil_fwd_kernel<KIND, XT, TT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            configured = true;
+        }
+        pil_fwd_kernel<KIND, XT, TT, true><<<blocks, kThreads, kSmemPerBlock, s>>>(a);
+    } else {
         pil_fwd_kernel<KIND, XT, TT, false><<<blocks, kThreads, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
 template <int KIND, typename XT>
@@ -822,10 +1247,16 @@ static cudaError_t launch_fwd_x(const FwdArgs& a, int x_dtype, int t_dtype, bool
 
 template <int KIND, typename XT, typename TT>
 static cudaError_t launch_bwd_a(const BwdArgs& a, bool aligned, int blocks, cudaStream_t s) {
-    if (aligned)
-        pil_bwd_kernel<KIND, XT, TT, true><<<blocks, kThreads, 0, s>>>(a);
-    else
+    if (aligned) {
+        static bool configured = false;  // per template instantiation
+        if (!configured) {
+            cudaFuncSetAttribute(pil_bwd_kernel<KIND, XT, TT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            configured = true;
+        }
+        pil_bwd_kernel<KIND, XT, TT, true><<<blocks, kThreads, kSmemPerBlock, s>>>(a);
+    } else {
         pil_bwd_kernel<KIND, XT, TT, false><<<blocks, kThreads, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
 template <int KIND, typename XT>

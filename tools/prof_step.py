@@ -15,13 +15,17 @@ from physics_informed_image_segmentation_b200 import _lib, functional as Fn  # n
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg3")
-ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--rps-fwd", type=int, default=0)
 ap.add_argument("--rps-bwd", type=int, default=0)
 ap.add_argument("--kind", type=int, default=1)
+ap.add_argument("--shape", default="")
 a = ap.parse_args()
 B, H, W, name = bench.WORKLOADS[a.workload]
+if a.shape:
+    B, H, W = (int(v) for v in a.shape.split("x"))
+    name = a.shape
 dev = torch.device("cuda:0")
 dt = torch.float32 if a.dtype == "f32" else torch.bfloat16
 z, t = bench.synth(B, H, W, 1234, dev, dt)
@@ -32,18 +36,18 @@ p = P.LossParams(**bench.STAGE2)
 sums = torch.empty(8, dtype=torch.float64, device=dev)
 rep = torch.empty(8, dtype=torch.float32, device=dev)
 _lib.lib().pil_set_tuning(a.rps_fwd, a.rps_bwd)
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-fm, bm = [], []
-for k in range(a.steps + 3):
-    ev[0].record()
+n_it = a.steps + 3
+ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_it)]
+torch.cuda.synchronize()
+for k in range(n_it):  # no host sync inside: the CPU runs ahead, intervals are pure GPU time
+    ev[k][0].record()
     Fn.forward_sums(z, t, p, a.kind, sums=sums, report=rep)
-    ev[1].record()
+    ev[k][1].record()
     Fn.backward_grad(z, t, p, a.kind, sums, z.numel(), out=g)
-    ev[2].record()
-    torch.cuda.synchronize()
-    if k >= 3:
-        fm.append(ev[0].elapsed_time(ev[1]))
-        bm.append(ev[1].elapsed_time(ev[2]))
+    ev[k][2].record()
+torch.cuda.synchronize()
+fm = [ev[k][0].elapsed_time(ev[k][1]) for k in range(3, n_it)]
+bm = [ev[k][1].elapsed_time(ev[k][2]) for k in range(3, n_it)]
 info = Fn.launch_info()
 n = z.numel()
 esz = z.element_size()
