@@ -138,6 +138,37 @@ int pil_backward(const void* x, const void* t, void* grad, int64_t B, int64_t H,
                  void* stream);
 
 /*
+ * Training-step split (what `loss = criterion(x, t); loss.backward()` of src/train.py:117,:163 costs
+ * when both halves are known to run): the stencils are evaluated ONCE, in the backward kernel.
+ *
+ *   pil_forward_pointwise     flat streaming kernel, only the sums that need no neighbours:
+ *                             sums = {I, P, T, sum bce, 0, sum u^2(1-u)^2/eps, n_invalid, n_pixels}
+ *   (data parallel: all-reduce sums here -- the gradient needs the global I, P, T)
+ *   pil_backward_accumulate   pil_backward + the two stencil sums of this shard:
+ *                             stencil_sums = {0,0,0,0, sum r^2, (eps/2) sum(gx^2+gy^2), 0, 0}
+ *                             sums + stencil_sums is exactly what pil_forward returns.  If loss_out is
+ *                             given, the last block finalises the loss from global_sums + stencil_sums
+ *                             (single shard); data parallel callers all-reduce stencil_sums and call
+ *                             pil_finalize instead.
+ *   pil_loss_fwd_bwd          the two above back to back for a single shard (upstream gradient 1):
+ *                             writes grad, the complete sums and the loss report.
+ *   pil_scale_gradient        grad *= *upstream on the device; returns immediately (no memory traffic)
+ *                             when *upstream == 1, the loss.backward() case.
+ */
+int pil_forward_pointwise(const void* x, const void* t, int64_t B, int64_t H, int64_t W,
+                          int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                          double* sums, void* workspace, size_t workspace_bytes, void* stream);
+int pil_backward_accumulate(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W,
+                            int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                            const double* global_sums, int64_t n_global, const float* upstream, float grad_scale,
+                            double* stencil_sums, float* loss_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int pil_loss_fwd_bwd(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W,
+                     int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                     double* sums, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+int pil_scale_gradient(void* grad, int dtype, int64_t n, const float* upstream, void* stream);
+
+/*
  * The PDERegularization operators a caller can use on their own (fp32 maps):
  *   pil_laplacian            compute_laplacian              src/pde.py:49-79
  *   pil_laplacian_adjoint    its autograd backward (transpose of the reflect-Laplacian)

@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pil.h"
 
@@ -34,7 +35,7 @@ constexpr int kStripCols = kOutLanes * kVec;  // 120 output columns per warp
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kFwdMinBlocks = 7;  // 32 warps / SM, <= 64 registers
-constexpr int kBwdMinBlocks = 5;  // 24 warps / SM, <= 85 registers
+constexpr int kBwdMinBlocks = 4;  // 24 warps / SM, <= 85 registers
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kLogClampLog2 = -100.0f * kLog2e;  // nn.BCELoss clamps ln() at -100
@@ -295,12 +296,18 @@ __device__ __forceinline__ float4 act4(float4 v) {
 // ------------------------------------------------------------------------------------------------
 // geometry shared by host and device
 // ------------------------------------------------------------------------------------------------
+// The B*H image rows of a shard are cut into `groups` equal ranges (to +-1 row; a range may straddle
+// an image boundary and is then processed as two segments).  Group g is processed by `strips` warps,
+// one per 120-column strip, so the warps of a group sweep full rows together (DRAM page locality).
+// groups*strips is sized to the number of warps the grid keeps resident, so every SM gets the same
+// number of blocks and all warps finish together (the kernels are not purely HBM-bound, so an SM with
+// one block more than its neighbour would otherwise be the critical path).
 struct Geo {
     int B, H, W;
-    int strips;         // warps per row band = ceil(W / 120)
-    int segs;           // row segments per image
-    int rps;            // rows per segment
-    long long tasks;    // B * segs * strips warp-tasks
+    int strips;            // warps per row band = ceil(W / 120)
+    long long groups;      // row ranges
+    long long total_rows;  // B * H
+    long long tasks;       // groups * strips warp-tasks
 };
 
 struct FwdArgs {
@@ -325,6 +332,14 @@ struct BwdArgs {
     float grad_scale;
     long long n_global;
     PilParams p;
+    int reverse;  // walk the shard back to front (L2 reuse after the pointwise forward)
+    // accumulate mode (pil_backward_accumulate): the stencil sums the pointwise forward left out
+    int accumulate;
+    double* partials;
+    unsigned int* ticket;
+    double* stencil_sums;  // out: {0,0,0,0, sum r^2, (eps/8) sum(dx^2+dy^2), 0, 0} of this shard
+    float* loss_out;       // optional: finalize(gsums + stencil_sums) as if this shard were the batch
+    double* total_sums;    // optional: gsums + stencil_sums (may alias gsums: written by the last block only)
 };
 
 __device__ __forceinline__ void finalize_device(const double* s, double n, const PilParams& p, float* out) {
@@ -343,6 +358,87 @@ __device__ __forceinline__ void finalize_device(const double* s, double n, const
     out[5] = (float)s[6];
     out[6] = 0.f;
     out[7] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic two-level reduction of the 8 per-thread accumulators:
+//   warp shuffles -> per-block doubles in `partials` -> the LAST block to finish (ticket) adds all
+//   per-block partials in a fixed order, so the result does not depend on block scheduling.
+// Returns true in the last block only; there thread 0 holds the totals in out[].  The caller resets
+// *ticket to 0 when it is done (so the workspace is reusable by the next launch on the stream).
+// accumulator layout: 0 I, 1 P, 2 T, 3 bce (log2 units, un-negated), 4 r^2, 5 dx^2+dy^2, 6 (uv)^2, 7 #invalid
+// ------------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ bool reduce_to_last_block(const float* acc, double* partials, unsigned int* ticket, double* out) {
+    constexpr int kWarps = THREADS / 32;
+    __shared__ double s_part[kWarps][PIL_NSUMS];
+    __shared__ double s_red[THREADS];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][k] = (double)v;
+    }
+    __syncthreads();
+    if (threadIdx.x < PIL_NSUMS) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += s_part[w][threadIdx.x];
+        partials[(long long)blockIdx.x * PIL_NSUMS + threadIdx.x] = v;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(ticket, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    {
+        // THREADS/8 row-groups x 8 components, 8 independent L2 loads in flight per thread, fixed order
+        constexpr int kGroups = THREADS / 8, kIlp = 8;
+        const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
+        const long long nb = gridDim.x;
+        double v = 0.0;
+        long long blk = j;
+        for (; blk + (kIlp - 1) * kGroups < nb; blk += kIlp * kGroups) {
+            double w[kIlp];
+#pragma unroll
+            for (int q = 0; q < kIlp; ++q) w[q] = __ldcg(partials + (blk + q * kGroups) * PIL_NSUMS + c);
+#pragma unroll
+            for (int q = 0; q < kIlp; ++q) v += w[q];
+        }
+        for (; blk < nb; blk += kGroups) v += __ldcg(partials + blk * PIL_NSUMS + c);
+        s_red[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < PIL_NSUMS) {
+        double v = 0.0;
+        for (int j = 0; j < THREADS / 8; ++j) v += s_red[j * 8 + threadIdx.x];
+        s_red[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < PIL_NSUMS; ++k) out[k] = s_red[k];
+    }
+    return true;
+}
+
+// raw accumulator totals -> the sums vector of include/pil.h
+__device__ __forceinline__ void sums_from_raw(const double* raw, double eps, double n_pixels, double* s) {
+    s[0] = raw[0];
+    s[1] = raw[1];
+    s[2] = raw[2];
+    s[3] = -(double)kLn2 * raw[3];                 // back from log2 units, BCE sign
+    s[4] = raw[4];
+    s[5] = (eps / 8.0) * raw[5] + raw[6] / eps;    // (eps/2)*(dx/2)^2 ... + (uv)^2/eps
+    s[6] = raw[7];
+    s[7] = n_pixels;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -494,11 +590,9 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
 
     if (task < g.tasks) {
         const int strip = (int)(task % g.strips);
-        const long long tmp = task / g.strips;
-        const int seg = (int)(tmp % g.segs);
-        const int b = (int)(tmp / g.segs);
-        const int r0 = seg * g.rps;
-        const int r1 = min(r0 + g.rps, g.H);
+        const long long grp = task / g.strips;
+        long long pos = (g.total_rows * grp) / g.groups;              // flattened image row b*H + r
+        const long long end = (g.total_rows * (grp + 1)) / g.groups;
         const int H = g.H, W = g.W;
         const int col0 = strip * kStripCols + (lane - 1) * kVec;
         const bool out_lane = (lane >= 1) && (lane <= kOutLanes);
@@ -510,6 +604,12 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
 #pragma unroll
             for (int p = 0; p < 4; ++p) fr.m[p] = (out_lane && col0 + p >= 0 && col0 + p < W) ? 1.0f : 0.0f;
         }
+#pragma unroll 1
+      while (pos < end) {  // one segment per image the range touches (normally one, at most a few)
+        const int b = (int)(pos / H);
+        const int r0 = (int)(pos - (long long)b * H);
+        const int r1 = (int)min((long long)H, (long long)r0 + (end - pos));
+        pos += r1 - r0;
 
         // per-image base pointers at this thread's column; rows are addressed with 32-bit offsets
         const int coff = ALIGNED ? cx.colc : 0;
@@ -578,7 +678,6 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
                 U1 = U2;
             }
             cp_async_wait<0>();
-            fr.fold_packed();
         } else {
             // prologue: rows r0-1, r0 become u; rows r0+1, r0+2 and targets r0, r0+1 are in flight.
             // Two fetch slots (A,B) alternate: iteration i consumes the slot holding map row i+1 / target
@@ -633,8 +732,10 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
             }
 
         }
+      }  // segments
 
         if constexpr (ALIGNED) {
+            fr.fold_packed();
             if (!counted) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) fr.acc[k] = 0.f;
@@ -642,63 +743,105 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
         }
     }
 
-    // ---- block reduction: warp shuffles, then 4 warps through shared memory --------------------
-    __shared__ double s_part[kWarpsPerBlock][PIL_NSUMS];
-    __shared__ bool s_last;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        float v = fr.acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_part[warp][k] = (double)v;
-    }
-    __syncthreads();
-    if (threadIdx.x < PIL_NSUMS) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerBlock; ++w) v += s_part[w][threadIdx.x];
-        A.partials[(long long)blockIdx.x * PIL_NSUMS + threadIdx.x] = v;
-        __threadfence();
-    }
-    __syncthreads();
+    // ---- deterministic cross-block reduction; the last block finalises --------------------------
+    double raw[PIL_NSUMS];
+    if (!reduce_to_last_block<kThreads>(fr.acc, A.partials, A.ticket, raw)) return;
     if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(A.ticket, 1u);
-        s_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-
-    // ---- last block: fixed-order sum of all per-block partials (deterministic) -----------------
-    __threadfence();
-    __shared__ double s_red[kThreads];
-    {
-        const int c = threadIdx.x & 7, j = threadIdx.x >> 3;  // 16 row-groups x 8 components
-        double v = 0.0;
-        for (long long blk = j; blk < gridDim.x; blk += kThreads / 8)
-            v += __ldcg(A.partials + blk * PIL_NSUMS + c);
-        s_red[threadIdx.x] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < PIL_NSUMS) {
-        double v = 0.0;
-        for (int j = 0; j < kThreads / 8; ++j) v += s_red[j * 8 + threadIdx.x];
-        s_red[threadIdx.x] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double eps = A.p.epsilon;
         double s[PIL_NSUMS];
-        s[0] = s_red[0];
-        s[1] = s_red[1];
-        s[2] = s_red[2];
-        s[3] = -(double)kLn2 * s_red[3];                       // back from log2 units, BCE sign
-        s[4] = s_red[4];
-        s[5] = (eps / 8.0) * s_red[5] + s_red[6] / eps;        // (eps/2)*(dx/2)^2 ... + W/eps
-        s[6] = s_red[7];
-        s[7] = (double)g.B * (double)g.H * (double)g.W;
+        sums_from_raw(raw, A.p.epsilon, (double)g.B * (double)g.H * (double)g.W, s);
 #pragma unroll
         for (int k = 0; k < PIL_NSUMS; ++k) A.sums[k] = s[k];
         if (A.loss_out != nullptr) finalize_device(s, s[7], A.p, A.loss_out);
+        *A.ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1L: pointwise forward ("light"): only the sums that do NOT need neighbours -- I, P, T, the BCE
+// terms and the double well -- as a flat, fully coalesced stream over the shard (no halo lanes, no
+// row structure, 8 B/px read once).  Used by the training path, where the backward kernel visits
+// every stencil anyway and accumulates sum r^2 and sum |grad u|^2 there (pil_backward_accumulate),
+// so the 5-point stencils are evaluated once per step instead of twice.
+// ------------------------------------------------------------------------------------------------
+constexpr long long kMaxPointBlocks = 2048;  // grid cap of the pointwise forward (workspace sizing)
+constexpr int kPointThreads = 256;
+constexpr int kPointUnroll = 4;  // float4 pairs in flight per thread
+
+struct PointArgs {
+    const void* x;
+    const void* t;
+    long long n;             // pixels in the shard
+    double* partials;
+    unsigned int* ticket;
+    double* sums;
+    PilParams p;
+};
+
+template <int KIND, typename XT, typename TT, bool ALIGNED>
+__global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const PointArgs A) {
+    FwdRow<KIND, true> fr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fr.acc[k] = 0.f;
+    fr.init_packed();
+    const long long tid = (long long)blockIdx.x * kPointThreads + threadIdx.x;
+    const long long stride = (long long)gridDim.x * kPointThreads;
+    const XT* x = reinterpret_cast<const XT*>(A.x);
+    const TT* t = reinterpret_cast<const TT*>(A.t);
+    if constexpr (ALIGNED) {
+        const long long n4 = A.n >> 2;  // n % 4 == 0 on this path
+        long long i = tid;
+        for (; i + (kPointUnroll - 1) * stride < n4; i += kPointUnroll * stride) {
+            float4 xv[kPointUnroll], tv[kPointUnroll];
+#pragma unroll
+            for (int q = 0; q < kPointUnroll; ++q) {
+                xv[q] = ld4<XT>(x + 4 * (i + q * stride));
+                tv[q] = ld4<TT>(t + 4 * (i + q * stride));
+            }
+#pragma unroll
+            for (int q = 0; q < kPointUnroll; ++q) fr.point4(xv[q], tv[q], true);
+        }
+        {   // last, partial batch: still issue every load before the first use
+            float4 xv[kPointUnroll], tv[kPointUnroll];
+#pragma unroll
+            for (int q = 0; q < kPointUnroll; ++q) {
+                if (i + q * stride < n4) {
+                    xv[q] = ld4<XT>(x + 4 * (i + q * stride));
+                    tv[q] = ld4<TT>(t + 4 * (i + q * stride));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kPointUnroll; ++q)
+                if (i + q * stride < n4) fr.point4(xv[q], tv[q], true);
+        }
+        fr.fold_packed();
+    } else {
+        // scalar path (odd sizes / unaligned bases): pairs (2i, 2i+1); an odd last pixel is paired with
+        // itself and the pair's contribution halved exactly (every accumulated term is per-pixel additive)
+        const long long n2 = A.n >> 1;
+        for (long long i = tid; i < n2; i += stride) {
+            fr.point2(make_float2(ld1<XT>(x + 2 * i), ld1<XT>(x + 2 * i + 1)),
+                      make_float2(ld1<TT>(t + 2 * i), ld1<TT>(t + 2 * i + 1)), true);
+        }
+        fr.fold_packed();
+        if ((A.n & 1) && tid == 0) {
+            FwdRow<KIND, true> one;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) one.acc[k] = 0.f;
+            one.init_packed();
+            const float xl = ld1<XT>(x + A.n - 1), tl = ld1<TT>(t + A.n - 1);
+            one.point2(make_float2(xl, xl), make_float2(tl, tl), true);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) fr.acc[k] += one.pa[k].x;
+            fr.acc[7] += 0.5f * one.acc[7];
+        }
+    }
+    double raw[PIL_NSUMS];
+    if (!reduce_to_last_block<kPointThreads>(fr.acc, A.partials, A.ticket, raw)) return;
+    if (threadIdx.x == 0) {
+        double sv[PIL_NSUMS];
+        sums_from_raw(raw, A.p.epsilon, (double)A.n, sv);
+#pragma unroll
+        for (int k = 0; k < PIL_NSUMS; ++k) A.sums[k] = sv[k];
         *A.ticket = 0u;
     }
 }
@@ -717,12 +860,46 @@ struct BwdCoef {
     float a1, c0;        // r = u*(u*(a1 - u) + c0) + D*(sum of 4 neighbours),  a1 = 1+a, c0 = -a - 4D
 };
 
+// accumulate mode: reduce the stencil sums across the grid; the last block publishes them and,
+// if asked, assembles the loss from (global pointwise sums + these) -- src/loss.py:144-160.
+__device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const float* acc) {
+    double raw[PIL_NSUMS];
+    if (!reduce_to_last_block<kThreads>(acc, A.partials, A.ticket, raw)) return;
+    if (threadIdx.x == 0) {
+        double sb[PIL_NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        sb[4] = raw[4];
+        sb[5] = (A.p.epsilon / 8.0) * raw[5];
+#pragma unroll
+        for (int k = 0; k < PIL_NSUMS; ++k) A.stencil_sums[k] = sb[k];
+        if (A.loss_out != nullptr || A.total_sums != nullptr) {
+            double tot[PIL_NSUMS];
+#pragma unroll
+            for (int k = 0; k < PIL_NSUMS; ++k) tot[k] = A.gsums[k] + sb[k];
+            if (A.loss_out != nullptr) finalize_device(tot, A.n_global > 0 ? (double)A.n_global : tot[7], A.p, A.loss_out);
+            if (A.total_sums != nullptr) {  // every block has read gsums long before the last one gets here
+#pragma unroll
+                for (int k = 0; k < PIL_NSUMS; ++k) A.total_sums[k] = tot[k];
+            }
+        }
+        *A.ticket = 0u;
+    }
+}
+
 template <int KIND, typename XT, typename TT, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const BwdArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Geo& g = A.g;
-    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    if (task >= g.tasks) return;
+    // Blocks are dispatched in index order; walking the shard from its END first lets the first wave
+    // hit the part of x and t that the pointwise forward (a front-to-back stream) left in L2.
+    const long long blk = A.reverse ? (long long)(gridDim.x - 1 - blockIdx.x) : (long long)blockIdx.x;
+    const long long task = blk * kWarpsPerBlock + warp;
+    if (task >= g.tasks) {
+        if (A.accumulate) {  // idle warp of the last block still takes part in the block reduction
+            const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            bwd_epilogue(A, zero);
+        }
+        return;
+    }
 
     // ---- coefficients from the global sums (double once per thread, then fp32) -----------------
     BwdCoef c;
@@ -749,11 +926,9 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
     }
 
     const int strip = (int)(task % g.strips);
-    const long long tmp = task / g.strips;
-    const int seg = (int)(tmp % g.segs);
-    const int b = (int)(tmp / g.segs);
-    const int r0 = seg * g.rps;
-    const int r1 = min(r0 + g.rps, g.H);
+    const long long grp = task / g.strips;
+    long long pos = (g.total_rows * grp) / g.groups;              // flattened image row b*H + r
+    const long long end = (g.total_rows * (grp + 1)) / g.groups;
     const int H = g.H, W = g.W;
     const int col0 = strip * kStripCols + (lane - 1) * kVec;
     const bool out_lane = (lane >= 1) && (lane <= kOutLanes);
@@ -773,7 +948,16 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         fc[p] = in ? ((cc == 0 || cc == W - 1) ? 2.0f : 1.0f) : 0.0f;
     }
     const bool store_vec = ALIGNED && out_lane && in_img;
+    // stencil sums of the rows this warp owns (accumulate mode): sum r^2 and sum dx^2+dy^2
+    f2 sr2 = make_float2(0.f, 0.f), sg2 = make_float2(0.f, 0.f);
+    float sr2s = 0.f, sg2s = 0.f;  // scalar path
 
+#pragma unroll 1
+  while (pos < end) {  // one segment per image the range touches (normally one, at most a few)
+    const int b = (int)(pos / H);
+    const int r0 = (int)(pos - (long long)b * H);
+    const int r1 = (int)min((long long)H, (long long)r0 + (end - pos));
+    pos += r1 - r0;
     const int coff = ALIGNED ? cx.colc : 0;
     const XT* xb = reinterpret_cast<const XT*>(A.x) + (long long)b * H * W + coff;
     const TT* tb = reinterpret_cast<const TT*>(A.t) + (long long)b * H * W + coff;
@@ -817,6 +1001,14 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
                 r[p] = fmaf(u, fmaf(u, c.a1 - u, c.c0), c.D * s4);
                 rc[p] = r[p];
                 dx[p] = e[p + 2] - e[p];
+            }
+            if (k >= r0 && k < r1) {  // rows this segment owns: the loss terms the light forward skipped
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float w = out_lane ? mc[p] : 0.0f, dy = vc[p] - va[p];
+                    sr2s = fmaf(r[p] * r[p], w, sr2s);
+                    sg2s = fmaf(dx[p] * dx[p] + dy * dy, w, sg2s);
+                }
             }
             if constexpr (ALIGNED) {
                 // only slots 0 and 3 can be an image-edge column or feed a neighbour lane; four
@@ -917,6 +1109,15 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
                 // r = D*(s4 - 4u) + u(1-u)(u-a), as a polynomial in u   (src/pde.py:73-77,:99,:120)
                 r[h] = fma2(u[h], fma2(u[h], sub2(bc(c.a1), u[h]), bc(c.c0)), mul2(bc(c.D), s4));
                 dx[h] = sub2(rt[h], lf[h]);
+            }
+            if (!CHECK || (k >= r0 && k < r1)) {  // rows this segment owns: loss terms the light forward skipped
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const f2 dy = sub2(vc[h], va[h]);
+                    sr2 = fma2(r[h], r[h], sr2);
+                    sg2 = fma2(dx[h], dx[h], sg2);
+                    sg2 = fma2(dy, dy, sg2);
+                }
             }
             // only slots 0 and 3 can be an image-edge column or feed a neighbour lane
             const float rc0 = r[0].x * fc[0], rc3 = r[1].y * fc[3];
@@ -1074,11 +1275,29 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
             G1 = G2;
         }
     }
+  }  // segments
+
+    if (!A.accumulate) return;  // uniform: plain pil_backward
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if constexpr (ALIGNED) {
+        if (store_vec) {
+            acc[4] = sr2.x + sr2.y;
+            acc[5] = sg2.x + sg2.y;
+        }
+    } else {
+        acc[4] = sr2s;
+        acc[5] = sg2s;
+    }
+    bwd_epilogue(A, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
 // small kernels: finalize, workspace init, stand-alone PDERegularization operators
 // ------------------------------------------------------------------------------------------------
+__global__ void pil_add_sums_kernel(double* sums, const double* extra) {
+    if (threadIdx.x < PIL_NSUMS && blockIdx.x == 0) sums[threadIdx.x] += extra[threadIdx.x];
+}
+
 __global__ void pil_finalize_kernel(const double* sums, long long n_global, PilParams p, float* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s[PIL_NSUMS];
@@ -1148,53 +1367,6 @@ __global__ void __launch_bounds__(256) pil_reaction_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static thread_local PilLaunchInfo t_info = {};
-static long long g_kernels_launched = 0;
-static int g_tune_fwd_rps = 0, g_tune_bwd_rps = 0;
-
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
-}
-
-// Choose rows-per-segment: every warp-task costs (rps + warm) row-iterations; tasks run in
-// ceil(tasks / resident_warps) rounds.  Minimise rounds * (rps + warm); ties go to longer segments.
-static Geo make_geo(int64_t B, int64_t H, int64_t W, int warm_rows, int resident_warps, int forced_rps) {
-    Geo g;
-    g.B = (int)B;
-    g.H = (int)H;
-    g.W = (int)W;
-    g.strips = (int)((W + kStripCols - 1) / kStripCols);
-    long long best_cost = -1;
-    int best_segs = 1;
-    if (forced_rps > 0) {
-        best_segs = (int)((H + forced_rps - 1) / forced_rps);
-    } else {
-        const int max_segs = (int)((H + 7) / 8);  // at least 8 rows per segment
-        for (int segs = 1; segs <= max_segs; ++segs) {
-            const int rps = (int)((H + segs - 1) / segs);
-            const int real_segs = (int)((H + rps - 1) / rps);
-            if (real_segs != segs) continue;
-            const long long tasks = (long long)B * g.strips * segs;
-            const long long rounds = (tasks + resident_warps - 1) / resident_warps;
-            const long long cost = rounds * (rps + warm_rows);
-            if (best_cost < 0 || cost < best_cost) {
-                best_cost = cost;
-                best_segs = segs;
-            }
-        }
-    }
-    g.rps = (int)((H + best_segs - 1) / best_segs);
-    g.segs = (int)((H + g.rps - 1) / g.rps);
-    g.tasks = (long long)B * g.strips * g.segs;
-    return g;
-}
-
 static int check_common(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
                         int x_kind, const PilParams* p) {
     if (!x || !t || !p) return PIL_ERR_NULL;
@@ -1217,64 +1389,212 @@ static bool is_aligned_case(const void* x, const void* t, const void* gptr, int6
     return true;
 }
 
-template <int KIND, typename XT, typename TT>
-static cudaError_t launch_fwd_a(const FwdArgs& a, bool aligned, int blocks, cudaStream_t s) {
-    if (aligned) {
-        static bool configured = false;  // per template instantiation
-        if (!configured) {
-            cudaFuncSetAttribute(pil_fwd_kernel<KIND, XT, TT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            configured = true;
-        }
-        pil_fwd_kernel<KIND, XT, TT, true><<<blocks, kThreads, kSmemPerBlock, s>>>(a);
+static thread_local PilLaunchInfo t_info = {};
+static long long g_kernels_launched = 0;
+static int g_tune_fwd_rps = 0, g_tune_bwd_rps = 0;
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// Size the row-range partition: one range-group per `strips` resident warps (waves = 1), so that
+// every SM holds the same number of blocks; never fewer than kMinRows rows per range.
+constexpr int kMinRows = 8;
+static Geo make_geo(int64_t B, int64_t H, int64_t W, int resident_blocks, int forced_rows, int waves) {
+    Geo g;
+    g.B = (int)B;
+    g.H = (int)H;
+    g.W = (int)W;
+    g.strips = (int)((W + kStripCols - 1) / kStripCols);
+    g.total_rows = (long long)B * H;
+    long long groups;
+    if (forced_rows > 0) {
+        groups = (g.total_rows + forced_rows - 1) / forced_rows;
     } else {
-        pil_fwd_kernel<KIND, XT, TT, false><<<blocks, kThreads, 0, s>>>(a);
+        const long long warps = (long long)resident_blocks * kWarpsPerBlock * (waves > 0 ? waves : 1);
+        groups = warps / g.strips;
+        const long long cap = (g.total_rows + kMinRows - 1) / kMinRows;
+        if (groups > cap) groups = cap;
     }
-    return cudaGetLastError();
+    if (groups < 1) groups = 1;
+    if (groups > g.total_rows) groups = g.total_rows;
+    g.groups = groups;
+    g.tasks = groups * g.strips;
+    return g;
 }
-template <int KIND, typename XT>
-static cudaError_t launch_fwd_t(const FwdArgs& a, int t_dtype, bool aligned, int blocks, cudaStream_t s) {
-    switch (t_dtype) {
-        case PIL_F32: return launch_fwd_a<KIND, XT, float>(a, aligned, blocks, s);
-        case PIL_BF16: return launch_fwd_a<KIND, XT, __nv_bfloat16>(a, aligned, blocks, s);
-        default: return launch_fwd_a<KIND, XT, uint8_t>(a, aligned, blocks, s);
+
+template <typename K>
+static int blocks_per_sm(K kernel, int smem_bytes) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem_bytes) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
+struct LaunchOut {
+    int blocks = 0, rows = 0;
+    int status = PIL_OK;  // PIL_ERR_WORKSPACE when the partials do not fit
+};
+// Rows per range the kernels like best (measured on B200, 64x1024^2 .. 128x2048^2): long enough to
+// amortise the warm-up rows and the pipeline fill of a segment, short enough that the hardware block
+// scheduler can still even out SM-to-SM speed differences with a few waves.
+constexpr int kTargetRowsFwd = 256, kTargetRowsBwd = 200;
+static int tuning_waves(bool bwd, int64_t B, int64_t H, int64_t W, int resident_blocks) {
+    static int forced[2] = {-1, -1};
+    if (forced[bwd] < 0) {
+        const char* e = getenv(bwd ? "PIL_WAVES_BWD" : "PIL_WAVES_FWD");
+        forced[bwd] = (e && atoi(e) > 0) ? atoi(e) : 0;
     }
-}
-template <int KIND>
-static cudaError_t launch_fwd_x(const FwdArgs& a, int x_dtype, int t_dtype, bool aligned, int blocks, cudaStream_t s) {
-    if (x_dtype == PIL_F32) return launch_fwd_t<KIND, float>(a, t_dtype, aligned, blocks, s);
-    return launch_fwd_t<KIND, __nv_bfloat16>(a, t_dtype, aligned, blocks, s);
+    if (forced[bwd] > 0) return forced[bwd];
+    const long long strips = (W + kStripCols - 1) / kStripCols;
+    const long long groups1 = (long long)resident_blocks * kWarpsPerBlock / strips;  // ranges in one wave
+    if (groups1 < 1) return 1;
+    const double rows1 = (double)(B * H) / (double)groups1;
+    const int target = bwd ? kTargetRowsBwd : kTargetRowsFwd;
+    int w = (int)(rows1 / target + 0.5);
+    return w < 1 ? 1 : w;
 }
 
 template <int KIND, typename XT, typename TT>
-static cudaError_t launch_bwd_a(const BwdArgs& a, bool aligned, int blocks, cudaStream_t s) {
-    if (aligned) {
-        static bool configured = false;  // per template instantiation
-        if (!configured) {
-            cudaFuncSetAttribute(pil_bwd_kernel<KIND, XT, TT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            configured = true;
+static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned, size_t partial_bytes_avail,
+                                cudaStream_t s, LaunchOut* out) {
+    static int per_sm_cache[2] = {0, 0};  // per template instantiation x {scalar, aligned} kernel
+    auto go = [&](auto kernel, int smem) -> cudaError_t {
+        int& per_sm = per_sm_cache[aligned ? 1 : 0];
+        if (per_sm == 0) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            per_sm = blocks_per_sm(kernel, smem);
         }
-        pil_bwd_kernel<KIND, XT, TT, true><<<blocks, kThreads, kSmemPerBlock, s>>>(a);
-    } else {
-        pil_bwd_kernel<KIND, XT, TT, false><<<blocks, kThreads, 0, s>>>(a);
-    }
-    return cudaGetLastError();
+        a.g = make_geo(B, H, W, sm_count() * per_sm, g_tune_fwd_rps, tuning_waves(false, B, H, W, sm_count() * per_sm));
+        out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
+        if ((size_t)out->blocks * PIL_NSUMS * sizeof(double) > partial_bytes_avail) {
+            out->status = PIL_ERR_WORKSPACE;
+            return cudaSuccess;
+        }
+        kernel<<<out->blocks, kThreads, smem, s>>>(a);
+        return cudaGetLastError();
+    };
+    if (aligned) return go(pil_fwd_kernel<KIND, XT, TT, true>, kSmemPerBlock);
+    return go(pil_fwd_kernel<KIND, XT, TT, false>, 0);
 }
+#define PIL_FWD_ARGS FwdArgs &a, int64_t B, int64_t H, int64_t W, bool aligned, size_t avail, cudaStream_t s, LaunchOut *out
+#define PIL_FWD_PASS a, B, H, W, aligned, avail, s, out
 template <int KIND, typename XT>
-static cudaError_t launch_bwd_t(const BwdArgs& a, int t_dtype, bool aligned, int blocks, cudaStream_t s) {
+static cudaError_t launch_fwd_t(int t_dtype, PIL_FWD_ARGS) {
     switch (t_dtype) {
-        case PIL_F32: return launch_bwd_a<KIND, XT, float>(a, aligned, blocks, s);
-        case PIL_BF16: return launch_bwd_a<KIND, XT, __nv_bfloat16>(a, aligned, blocks, s);
-        default: return launch_bwd_a<KIND, XT, uint8_t>(a, aligned, blocks, s);
+        case PIL_F32: return launch_fwd_a<KIND, XT, float>(PIL_FWD_PASS);
+        case PIL_BF16: return launch_fwd_a<KIND, XT, __nv_bfloat16>(PIL_FWD_PASS);
+        default: return launch_fwd_a<KIND, XT, uint8_t>(PIL_FWD_PASS);
     }
 }
 template <int KIND>
-static cudaError_t launch_bwd_x(const BwdArgs& a, int x_dtype, int t_dtype, bool aligned, int blocks, cudaStream_t s) {
-    if (x_dtype == PIL_F32) return launch_bwd_t<KIND, float>(a, t_dtype, aligned, blocks, s);
-    return launch_bwd_t<KIND, __nv_bfloat16>(a, t_dtype, aligned, blocks, s);
+static cudaError_t launch_fwd_x(int x_dtype, int t_dtype, PIL_FWD_ARGS) {
+    if (x_dtype == PIL_F32) return launch_fwd_t<KIND, float>(t_dtype, PIL_FWD_PASS);
+    return launch_fwd_t<KIND, __nv_bfloat16>(t_dtype, PIL_FWD_PASS);
+}
+
+template <int KIND, typename XT, typename TT>
+static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned, cudaStream_t s, LaunchOut* out) {
+    static int per_sm_cache[2] = {0, 0};  // per template instantiation x {scalar, aligned} kernel
+    auto go = [&](auto kernel, int smem) -> cudaError_t {
+        int& per_sm = per_sm_cache[aligned ? 1 : 0];
+        if (per_sm == 0) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            per_sm = blocks_per_sm(kernel, smem);
+        }
+        a.g = make_geo(B, H, W, sm_count() * per_sm, g_tune_bwd_rps, tuning_waves(true, B, H, W, sm_count() * per_sm));
+        out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
+        kernel<<<out->blocks, kThreads, smem, s>>>(a);
+        return cudaGetLastError();
+    };
+    if (aligned) return go(pil_bwd_kernel<KIND, XT, TT, true>, kSmemPerBlock);
+    return go(pil_bwd_kernel<KIND, XT, TT, false>, 0);
+}
+#define PIL_BWD_ARGS BwdArgs &a, int64_t B, int64_t H, int64_t W, bool aligned, cudaStream_t s, LaunchOut *out
+#define PIL_BWD_PASS a, B, H, W, aligned, s, out
+template <int KIND, typename XT>
+static cudaError_t launch_bwd_t(int t_dtype, PIL_BWD_ARGS) {
+    switch (t_dtype) {
+        case PIL_F32: return launch_bwd_a<KIND, XT, float>(PIL_BWD_PASS);
+        case PIL_BF16: return launch_bwd_a<KIND, XT, __nv_bfloat16>(PIL_BWD_PASS);
+        default: return launch_bwd_a<KIND, XT, uint8_t>(PIL_BWD_PASS);
+    }
+}
+template <int KIND>
+static cudaError_t launch_bwd_x(int x_dtype, int t_dtype, PIL_BWD_ARGS) {
+    if (x_dtype == PIL_F32) return launch_bwd_t<KIND, float>(t_dtype, PIL_BWD_PASS);
+    return launch_bwd_t<KIND, __nv_bfloat16>(t_dtype, PIL_BWD_PASS);
+}
+
+template <int KIND, typename XT, typename TT>
+static cudaError_t launch_point_a(const PointArgs& a, bool aligned, cudaStream_t s, int* blocks_out) {
+    static int per_sm_cache[2] = {0, 0};
+    auto go = [&](auto kernel) -> cudaError_t {
+        int& per_sm = per_sm_cache[aligned ? 1 : 0];
+        if (per_sm == 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kPointThreads, 0) != cudaSuccess || n < 1) n = 1;
+            per_sm = n;
+        }
+        const long long work = aligned ? (a.n >> 2) : ((a.n + 1) >> 1);                  // thread-iterations
+        long long blocks = (work + (long long)kPointThreads * kPointUnroll - 1) / ((long long)kPointThreads * kPointUnroll);
+        const long long cap = (long long)sm_count() * per_sm;
+        if (blocks > cap) blocks = cap;
+        if (blocks > kMaxPointBlocks) blocks = kMaxPointBlocks;
+        if (blocks < 1) blocks = 1;
+        *blocks_out = (int)blocks;
+        kernel<<<(int)blocks, kPointThreads, 0, s>>>(a);
+        return cudaGetLastError();
+    };
+    if (aligned) return go(pil_point_kernel<KIND, XT, TT, true>);
+    return go(pil_point_kernel<KIND, XT, TT, false>);
+}
+template <int KIND, typename XT>
+static cudaError_t launch_point_t(int t_dtype, const PointArgs& a, bool aligned, cudaStream_t s, int* b) {
+    switch (t_dtype) {
+        case PIL_F32: return launch_point_a<KIND, XT, float>(a, aligned, s, b);
+        case PIL_BF16: return launch_point_a<KIND, XT, __nv_bfloat16>(a, aligned, s, b);
+        default: return launch_point_a<KIND, XT, uint8_t>(a, aligned, s, b);
+    }
+}
+template <int KIND>
+static cudaError_t launch_point_x(int x_dtype, int t_dtype, const PointArgs& a, bool aligned, cudaStream_t s, int* b) {
+    if (x_dtype == PIL_F32) return launch_point_t<KIND, float>(t_dtype, a, aligned, s, b);
+    return launch_point_t<KIND, __nv_bfloat16>(t_dtype, a, aligned, s, b);
+}
+
+__global__ void __launch_bounds__(256) pil_scale_kernel(float* __restrict__ g, long long n4, const float* __restrict__ up) {
+    const float s = __ldg(up);
+    if (s == 1.0f) return;  // loss.backward() on the loss itself: nothing to do
+    float4* g4 = reinterpret_cast<float4*>(g);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = g4[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        g4[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) pil_scale_kernel_generic(void* __restrict__ g, int is_bf16, long long n, const float* __restrict__ up) {
+    const float s = __ldg(up);
+    if (s == 1.0f) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (is_bf16) {
+            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(g) + i;
+            *p = __float2bfloat16_rn(__bfloat162float(*p) * s);
+        } else {
+            reinterpret_cast<float*>(g)[i] *= s;
+        }
+    }
 }
 
 struct WorkspaceLayout {
-    size_t ticket_off, partials_off, total;
+    size_t ticket_off, scratch_off, partials_off, total;
 };
 static WorkspaceLayout workspace_layout(int64_t B, int64_t H, int64_t W) {
     // worst case number of forward blocks: 8-row segments
@@ -1283,8 +1603,9 @@ static WorkspaceLayout workspace_layout(int64_t B, int64_t H, int64_t W) {
     const long long blocks = (B * strips * segs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     WorkspaceLayout l;
     l.ticket_off = 0;
+    l.scratch_off = 64;   // PIL_NSUMS doubles of scratch (pil_loss_fwd_bwd)
     l.partials_off = 256;
-    l.total = l.partials_off + (size_t)blocks * PIL_NSUMS * sizeof(double);
+    l.total = l.partials_off + (size_t)(blocks > kMaxPointBlocks ? blocks : kMaxPointBlocks) * PIL_NSUMS * sizeof(double);
     return l;
 }
 
@@ -1343,11 +1664,9 @@ int pil_forward(const void* x, const void* t, int64_t B, int64_t H, int64_t W, i
     const WorkspaceLayout wl = workspace_layout(B, H, W);
     if (workspace_bytes < wl.total || ((uintptr_t)workspace % 8)) return PIL_ERR_WORKSPACE;
 
-    const int resident = sm_count() * kFwdMinBlocks * kWarpsPerBlock;
     FwdArgs a;
     a.x = x;
     a.t = t;
-    a.g = make_geo(B, H, W, /*warm_rows=*/2, resident, g_tune_fwd_rps);
     a.D = (float)p->diffusion_coeff;
     a.a = (float)p->reaction_threshold;
     a.ticket = reinterpret_cast<unsigned int*>((char*)workspace + wl.ticket_off);
@@ -1355,19 +1674,21 @@ int pil_forward(const void* x, const void* t, int64_t B, int64_t H, int64_t W, i
     a.sums = sums;
     a.loss_out = loss_out;
     a.p = *p;
-    const int blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    if (wl.partials_off + (size_t)blocks * PIL_NSUMS * sizeof(double) > workspace_bytes) return PIL_ERR_WORKSPACE;
     const bool aligned = is_aligned_case(x, t, nullptr, W, x_dtype, t_dtype);
     cudaStream_t s = (cudaStream_t)stream;
+    const size_t avail = workspace_bytes - wl.partials_off;
+    LaunchOut lo;
     cudaError_t e;
     switch (x_kind) {
-        case PIL_X_PROB: e = launch_fwd_x<PIL_X_PROB>(a, x_dtype, t_dtype, aligned, blocks, s); break;
-        case PIL_X_LOGITS_SIGMOID: e = launch_fwd_x<PIL_X_LOGITS_SIGMOID>(a, x_dtype, t_dtype, aligned, blocks, s); break;
-        default: e = launch_fwd_x<PIL_X_LOGITS_TANH>(a, x_dtype, t_dtype, aligned, blocks, s); break;
+        case PIL_X_PROB: e = launch_fwd_x<PIL_X_PROB>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo); break;
+        case PIL_X_LOGITS_SIGMOID: e = launch_fwd_x<PIL_X_LOGITS_SIGMOID>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo); break;
+        default: e = launch_fwd_x<PIL_X_LOGITS_TANH>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo); break;
     }
+    if (lo.status != PIL_OK) return lo.status;
+    const int blocks = lo.blocks;
     t_info.fwd_blocks = blocks;
     t_info.fwd_threads = kThreads;
-    t_info.fwd_rows_per_segment = a.g.rps;
+    t_info.fwd_rows_per_segment = lo.rows;
     t_info.fwd_aligned = aligned ? 1 : 0;
     ++g_kernels_launched;
     return (int)e;
@@ -1380,40 +1701,142 @@ int pil_finalize(const double* sums, int64_t n_global, const PilParams* p, float
     return (int)cudaGetLastError();
 }
 
-int pil_backward(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
-                 int x_kind, const PilParams* p, const double* global_sums, int64_t n_global, const float* upstream,
-                 float grad_scale, void* stream) {
+static int backward_impl(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                         int x_kind, const PilParams* p, const double* global_sums, int64_t n_global, const float* upstream,
+                         float grad_scale, double* stencil_sums, float* loss_out, double* total_sums, void* acc_ws,
+                         void* stream) {
     int st = check_common(x, t, B, H, W, x_dtype, t_dtype, x_kind, p);
     if (st != PIL_OK) return st;
     if (!grad || !global_sums) return PIL_ERR_NULL;
     if ((uintptr_t)grad % dtype_size(x_dtype)) return PIL_ERR_ALIGNMENT;
 
-    const int resident = sm_count() * kBwdMinBlocks * kWarpsPerBlock;
     BwdArgs a;
     a.x = x;
     a.t = t;
     a.grad = grad;
-    a.g = make_geo(B, H, W, /*warm_rows=*/4, resident, g_tune_bwd_rps);
     a.gsums = global_sums;
     a.upstream = upstream;
     a.grad_scale = grad_scale;
     a.n_global = (long long)n_global;
     a.p = *p;
-    const int blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    a.accumulate = acc_ws != nullptr ? 1 : 0;
+    {
+        static int rev = -1;
+        if (rev < 0) {
+            const char* e = getenv("PIL_BWD_REVERSE");
+            rev = e ? atoi(e) : 1;
+        }
+        a.reverse = rev;
+    }
+    a.partials = nullptr;
+    a.ticket = nullptr;
+    a.stencil_sums = stencil_sums;
+    a.loss_out = loss_out;
+    a.total_sums = total_sums;
+    if (a.accumulate) {
+        const WorkspaceLayout wl = workspace_layout(B, H, W);
+        a.ticket = reinterpret_cast<unsigned int*>((char*)acc_ws + wl.ticket_off);
+        a.partials = reinterpret_cast<double*>((char*)acc_ws + wl.partials_off);
+    }
     const bool aligned = is_aligned_case(x, t, grad, W, x_dtype, t_dtype);
     cudaStream_t s = (cudaStream_t)stream;
+    LaunchOut lo;
     cudaError_t e;
     switch (x_kind) {
-        case PIL_X_PROB: e = launch_bwd_x<PIL_X_PROB>(a, x_dtype, t_dtype, aligned, blocks, s); break;
-        case PIL_X_LOGITS_SIGMOID: e = launch_bwd_x<PIL_X_LOGITS_SIGMOID>(a, x_dtype, t_dtype, aligned, blocks, s); break;
-        default: e = launch_bwd_x<PIL_X_LOGITS_TANH>(a, x_dtype, t_dtype, aligned, blocks, s); break;
+        case PIL_X_PROB: e = launch_bwd_x<PIL_X_PROB>(x_dtype, t_dtype, a, B, H, W, aligned, s, &lo); break;
+        case PIL_X_LOGITS_SIGMOID: e = launch_bwd_x<PIL_X_LOGITS_SIGMOID>(x_dtype, t_dtype, a, B, H, W, aligned, s, &lo); break;
+        default: e = launch_bwd_x<PIL_X_LOGITS_TANH>(x_dtype, t_dtype, a, B, H, W, aligned, s, &lo); break;
     }
+    const int blocks = lo.blocks;
     t_info.bwd_blocks = blocks;
     t_info.bwd_threads = kThreads;
-    t_info.bwd_rows_per_segment = a.g.rps;
+    t_info.bwd_rows_per_segment = lo.rows;
     t_info.bwd_aligned = aligned ? 1 : 0;
     ++g_kernels_launched;
     return (int)e;
+}
+
+int pil_backward(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                 int x_kind, const PilParams* p, const double* global_sums, int64_t n_global, const float* upstream,
+                 float grad_scale, void* stream) {
+    return backward_impl(x, t, grad, B, H, W, x_dtype, t_dtype, x_kind, p, global_sums, n_global, upstream, grad_scale,
+                         nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int pil_backward_accumulate(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype,
+                            int t_dtype, int x_kind, const PilParams* p, const double* global_sums, int64_t n_global,
+                            const float* upstream, float grad_scale, double* stencil_sums, float* loss_out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    if (!stencil_sums || !workspace) return PIL_ERR_NULL;
+    if (B >= 1 && H >= 2 && W >= 2) {
+        const WorkspaceLayout wl = workspace_layout(B, H, W);
+        if (workspace_bytes < wl.total || ((uintptr_t)workspace % 8)) return PIL_ERR_WORKSPACE;
+    }
+    return backward_impl(x, t, grad, B, H, W, x_dtype, t_dtype, x_kind, p, global_sums, n_global, upstream, grad_scale,
+                         stencil_sums, loss_out, nullptr, workspace, stream);
+}
+
+int pil_forward_pointwise(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                          int x_kind, const PilParams* p, double* sums, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    int st = check_common(x, t, B, H, W, x_dtype, t_dtype, x_kind, p);
+    if (st != PIL_OK) return st;
+    if (!sums || !workspace) return PIL_ERR_NULL;
+    const WorkspaceLayout wl = workspace_layout(B, H, W);
+    if (workspace_bytes < wl.total || ((uintptr_t)workspace % 8)) return PIL_ERR_WORKSPACE;
+    PointArgs a;
+    a.x = x;
+    a.t = t;
+    a.n = (long long)B * H * W;
+    a.ticket = reinterpret_cast<unsigned int*>((char*)workspace + wl.ticket_off);
+    a.partials = reinterpret_cast<double*>((char*)workspace + wl.partials_off);
+    a.sums = sums;
+    a.p = *p;
+    // flat stream: only total size and base alignment matter
+    const bool aligned = (a.n % 4 == 0) && is_aligned_case(x, t, nullptr, 4, x_dtype, t_dtype);
+    cudaStream_t s = (cudaStream_t)stream;
+    int blocks = 0;
+    cudaError_t e;
+    switch (x_kind) {
+        case PIL_X_PROB: e = launch_point_x<PIL_X_PROB>(x_dtype, t_dtype, a, aligned, s, &blocks); break;
+        case PIL_X_LOGITS_SIGMOID: e = launch_point_x<PIL_X_LOGITS_SIGMOID>(x_dtype, t_dtype, a, aligned, s, &blocks); break;
+        default: e = launch_point_x<PIL_X_LOGITS_TANH>(x_dtype, t_dtype, a, aligned, s, &blocks); break;
+    }
+    t_info.fwd_blocks = blocks;
+    t_info.fwd_threads = kPointThreads;
+    t_info.fwd_rows_per_segment = 0;
+    t_info.fwd_aligned = aligned ? 1 : 0;
+    ++g_kernels_launched;
+    return (int)e;
+}
+
+int pil_loss_fwd_bwd(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                     int x_kind, const PilParams* p, double* sums, float* loss_out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (!loss_out) return PIL_ERR_NULL;
+    int st = pil_forward_pointwise(x, t, B, H, W, x_dtype, t_dtype, x_kind, p, sums, workspace, workspace_bytes, stream);
+    if (st != PIL_OK) return st;
+    const WorkspaceLayout wl = workspace_layout(B, H, W);
+    double* scratch = reinterpret_cast<double*>((char*)workspace + wl.scratch_off);
+    if (B >= 1 && H >= 2 && W >= 2 && (workspace_bytes < wl.total || ((uintptr_t)workspace % 8))) return PIL_ERR_WORKSPACE;
+    // the backward's last block also writes sums := sums + stencil sums, so the caller ends up with the
+    // same vector pil_forward would have produced -- no extra launch
+    return backward_impl(x, t, grad, B, H, W, x_dtype, t_dtype, x_kind, p, sums, B * H * W, nullptr, 1.0f, scratch, loss_out,
+                         sums, workspace, stream);
+}
+
+int pil_scale_gradient(void* grad, int dtype, int64_t n, const float* upstream, void* stream) {
+    if (!grad || !upstream) return PIL_ERR_NULL;
+    if (n < 1) return PIL_ERR_SHAPE;
+    if (!(dtype == PIL_F32 || dtype == PIL_BF16)) return PIL_ERR_DTYPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = sm_count() * 8;
+    if (dtype == PIL_F32 && n % 4 == 0 && (uintptr_t)grad % 16 == 0)
+        pil_scale_kernel<<<blocks, 256, 0, s>>>((float*)grad, (long long)(n >> 2), upstream);
+    else
+        pil_scale_kernel_generic<<<blocks, 256, 0, s>>>(grad, dtype == PIL_BF16, (long long)n, upstream);
+    ++g_kernels_launched;
+    return (int)cudaGetLastError();
 }
 
 static int stencil_launch(int op, const float* u, const float* g, float* out, int64_t B, int64_t H, int64_t W,

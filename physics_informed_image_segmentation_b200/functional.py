@@ -183,6 +183,84 @@ def backward_grad(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, gs
     return out
 
 
+def forward_pointwise(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int,
+                      sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1L: the neighbour-free sums only (I, P, T, BCE, double well); flat streaming kernel."""
+    B, H, W = check_maps(x, t)
+    dev = x.device
+    if sums is None:
+        sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    ws = workspace(dev, B, H, W)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_forward_pointwise(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                                              ctypes.byref(cp), sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(st, "pil_forward_pointwise")
+    return sums
+
+
+def backward_accumulate(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, gsums: torch.Tensor, n_global: int,
+                        upstream: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                        out: Optional[torch.Tensor] = None, stencil_sums: Optional[torch.Tensor] = None,
+                        report: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K2 + the stencil sums the pointwise forward skipped.  Returns (grad, stencil_sums); when
+    `report` is given the kernel's last block also assembles the loss (single shard)."""
+    B, H, W = check_maps(x, t)
+    dev = x.device
+    if out is None:
+        out = torch.empty_like(x)
+    if stencil_sums is None:
+        stencil_sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    up_ptr = None
+    if upstream is not None:
+        if upstream.dtype != torch.float32 or upstream.numel() != 1 or upstream.device != dev:
+            upstream = upstream.to(device=dev, dtype=torch.float32).reshape(1)
+        up_ptr = upstream.data_ptr()
+    ws = workspace(dev, B, H, W)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_backward_accumulate(x.data_ptr(), t.data_ptr(), out.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t),
+                                                kind, ctypes.byref(cp), gsums.data_ptr(), int(n_global), up_ptr,
+                                                float(grad_scale), stencil_sums.data_ptr(),
+                                                report.data_ptr() if report is not None else None,
+                                                ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(st, "pil_backward_accumulate")
+    return out, stencil_sums
+
+
+def loss_fwd_bwd(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, grad: Optional[torch.Tensor] = None,
+                 sums: Optional[torch.Tensor] = None, report: Optional[torch.Tensor] = None):
+    """One training-step evaluation on a single shard: pointwise forward -> backward (+ stencil sums).
+    Returns (report float32[8], sums float64[8] -- the same vector pil_forward produces, grad like x)."""
+    B, H, W = check_maps(x, t)
+    dev = x.device
+    if grad is None:
+        grad = torch.empty_like(x)
+    if sums is None:
+        sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    if report is None:
+        report = torch.empty(PIL_NOUT, dtype=torch.float32, device=dev)
+    ws = workspace(dev, B, H, W)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_loss_fwd_bwd(x.data_ptr(), t.data_ptr(), grad.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                                         ctypes.byref(cp), sums.data_ptr(), report.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _stream_ptr(dev))
+    _lib.check(st, "pil_loss_fwd_bwd")
+    return report, sums, grad
+
+
+def scale_gradient(grad: torch.Tensor, upstream: torch.Tensor) -> torch.Tensor:
+    """grad *= upstream on the device, in place; free when upstream == 1 (plain loss.backward())."""
+    dev = grad.device
+    if upstream.dtype != torch.float32 or upstream.numel() != 1 or upstream.device != dev:
+        upstream = upstream.to(device=dev, dtype=torch.float32).reshape(1)
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_scale_gradient(grad.data_ptr(), _x_dtype(grad), grad.numel(), upstream.data_ptr(), _stream_ptr(dev))
+    _lib.check(st, "pil_scale_gradient")
+    return grad
+
+
 def launch_info() -> _lib.PilLaunchInfo:
     info = _lib.PilLaunchInfo()
     _lib.check(_lib.lib().pil_last_launch_info(ctypes.byref(info)), "pil_last_launch_info")
@@ -192,48 +270,64 @@ def launch_info() -> _lib.PilLaunchInfo:
 # ---------------------------------------------------------------------------------------------
 # autograd glue
 # ---------------------------------------------------------------------------------------------
-class _FusedLossFn(torch.autograd.Function):
-    """loss-report = K1(x, t) [-> all-reduce] ; dL/dx = K2(x, t, global sums).
+def _params_for(p: LossParams, which: int) -> LossParams:
+    """Weights that make the fused gradient the gradient of ONE report entry."""
+    if which == OUT_DICE:
+        return replace(p, dice_weight=1.0, bce_weight=0.0, pde_weight=0.0, phase_field_weight=0.0)
+    if which == OUT_BCE:
+        return replace(p, dice_weight=0.0, bce_weight=1.0, pde_weight=0.0, phase_field_weight=0.0)
+    if which == OUT_RD:
+        return replace(p, dice_weight=0.0, bce_weight=0.0, pde_weight=1.0, phase_field_weight=0.0)
+    if which == OUT_PF:
+        return replace(p, dice_weight=0.0, bce_weight=0.0, pde_weight=0.0, phase_field_weight=1.0)
+    return p
 
-    Returns the whole report vector (float32[8]); callers index the entry they want, so one forward
+
+class _FusedLossFn(torch.autograd.Function):
+    """Training path.  Both halves of `loss = criterion(x, t); loss.backward()` are known to run, so the
+    forward launches the pointwise sums kernel AND the backward kernel (which also accumulates the two
+    stencil sums): every 5-point stencil is evaluated once per step, and the loss report is complete
+    when forward returns.  backward() only applies the upstream scalar (a no-op kernel when it is 1).
+
+    Returns the requested report entry plus the whole report vector (float32[8]), so one evaluation
     serves the total loss AND the four logged components (reference src/train.py:120-150)."""
 
     @staticmethod
     def forward(ctx, x, t, p: LossParams, kind: int, which: int, group, ddp_average: bool):
         x_d = x.detach()
         t_d = t.detach()
-        distributed = group is not None
-        if distributed:
+        pg = _params_for(p, which)  # the gradient is that of the requested entry
+        if group is not None:
             import torch.distributed as dist
 
-            sums, _ = forward_sums(x_d, t_d, p, kind, finalize=False)
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-            n_global = -1  # read the all-reduced pixel count sums[7] on the device
-            report = finalize_report(sums, n_global, p)
             scale = float(dist.get_world_size(group)) if ddp_average else 1.0
+            sums = forward_pointwise(x_d, t_d, pg, kind)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)           # the gradient needs global I, P, T
+            grad, stencil = backward_accumulate(x_d, t_d, pg, kind, sums, -1, grad_scale=scale)
+            dist.all_reduce(stencil, op=dist.ReduceOp.SUM, group=group)        # only the loss VALUE needs these
+            sums = sums + stencil
+            report = finalize_report(sums, -1, p)
+            n_global = -1
         else:
-            sums, report = forward_sums(x_d, t_d, p, kind, finalize=True)
-            n_global = x_d.numel()
-            scale = 1.0
+            report, sums, grad = loss_fwd_bwd(x_d, t_d, pg, kind)
+            if pg is not p:
+                report = finalize_report(sums, x_d.numel(), p)
+            scale, n_global = 1.0, x_d.numel()
         ctx.save_for_backward(x_d, t_d, sums)
-        ctx.p, ctx.kind, ctx.which, ctx.n_global, ctx.scale = p, kind, which, n_global, scale
+        ctx.grad = grad
+        ctx.p, ctx.kind, ctx.n_global, ctx.scale = pg, kind, n_global, scale
         ctx.mark_non_differentiable(report)
         return report[which], report
 
     @staticmethod
     def backward(ctx, g_loss, _g_report):
+        grad = ctx.grad
+        if grad is not None:
+            ctx.grad = None  # the buffer is scaled in place, so it can be handed out once
+            return scale_gradient(grad, g_loss), None, None, None, None, None, None
+        # second backward through a retained graph: recompute from the saved global sums
         x, t, sums = ctx.saved_tensors
-        p = ctx.p
-        # differentiate the requested entry only: the total, or one component on its own
-        if ctx.which == OUT_DICE:
-            p = replace(p, dice_weight=1.0, bce_weight=0.0, pde_weight=0.0, phase_field_weight=0.0)
-        elif ctx.which == OUT_BCE:
-            p = replace(p, dice_weight=0.0, bce_weight=1.0, pde_weight=0.0, phase_field_weight=0.0)
-        elif ctx.which == OUT_RD:
-            p = replace(p, dice_weight=0.0, bce_weight=0.0, pde_weight=1.0, phase_field_weight=0.0)
-        elif ctx.which == OUT_PF:
-            p = replace(p, dice_weight=0.0, bce_weight=0.0, pde_weight=0.0, phase_field_weight=1.0)
-        grad = backward_grad(x, t, p, ctx.kind, sums, ctx.n_global, upstream=g_loss, grad_scale=ctx.scale)
+        grad = backward_grad(x, t, ctx.p, ctx.kind, sums, ctx.n_global, upstream=g_loss, grad_scale=ctx.scale)
         return grad, None, None, None, None, None, None
 
 

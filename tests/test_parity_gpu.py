@@ -301,3 +301,77 @@ def test_forced_segment_lengths_agree(Fn, po, dev):
                 assert rel_max(g, base[1]) < 1e-6
     finally:
         _lib.lib().pil_set_tuning(0, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# training-step split: pointwise forward + accumulating backward (pil_loss_fwd_bwd)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,kind", [((8, 256, 256), 1), ((3, 127, 129), 1), ((2, 3, 5), 0), ((1, 2, 2), 1),
+                                        ((5, 17, 36), 0), ((2, 70, 1024), 1), ((1, 33, 240), 2), ((1, 7, 1001), 1)])
+def test_split_step_equals_full_path_and_oracle(Fn, po, dev, shape, kind):
+    """pil_loss_fwd_bwd (stencils evaluated once, in the backward kernel) must give the same sums, loss
+    report and gradient as pil_forward + pil_backward, and match the oracle."""
+    z, t = iid_inputs(*shape, seed=sum(shape) + kind)
+    if kind == 2:
+        z = 0.5 * z
+    x = (torch.sigmoid(z) if kind == 0 else z).to(dev)
+    tt = t.to(dev)
+    p = lp(Fn, po.STAGE2)
+    rep_s, sums_s, g_s = Fn.loss_fwd_bwd(x, tt, p, kind)
+    sums_f, rep_f = Fn.forward_sums(x, tt, p, kind)
+    g_f = Fn.backward_grad(x, tt, p, kind, sums_f, x.numel())
+    torch.cuda.synchronize()
+    for k in range(6):
+        assert rel_scalar(sums_s[k].item(), sums_f[k].item()) < 2e-6, k
+    assert sums_s[6] == sums_f[6] and sums_s[7] == sums_f[7]
+    for k in range(5):
+        assert rel_scalar(rep_s[k].item(), rep_f[k].item()) < 2e-6, k
+    assert rel_max(g_s.cpu().numpy(), g_f.cpu().numpy()) < 2e-6
+    x64, t64 = x.cpu().numpy().astype(np.float64), t.numpy().astype(np.float64)
+    comps, og = po.loss_and_grad(x64, t64, po.STAGE2, kind)
+    for k in range(5):
+        assert rel_scalar(rep_s[k].item(), comps[k]) < TOL, k
+    assert rel_max(g_s.cpu().numpy(), og) < TOL and rel_l2(g_s.cpu().numpy(), og) < TOL
+
+
+def test_split_step_pieces_and_scaling(Fn, po, dev):
+    """the pieces a data-parallel caller uses: pointwise sums + stencil sums == full sums;
+    pil_scale_gradient is exact and leaves the buffer untouched for an upstream gradient of 1"""
+    z, t = blob_inputs(4, 64, 128, seed=77)
+    x, tt, p = z.to(dev), t.to(dev), lp(Fn, po.STAGE2)
+    sa = Fn.forward_pointwise(x, tt, p, 1)
+    assert sa[4].item() == 0.0 and sa[7].item() == x.numel()
+    g, sb = Fn.backward_accumulate(x, tt, p, 1, sa, x.numel())
+    assert all(sb[k].item() == 0.0 for k in (0, 1, 2, 3, 6, 7)) and sb[4].item() > 0 and sb[5].item() > 0
+    full, _ = Fn.forward_sums(x, tt, p, 1)
+    tot = sa + sb
+    for k in range(6):
+        assert rel_scalar(tot[k].item(), full[k].item()) < 2e-6, k
+    rep = Fn.finalize_report(tot, -1, p)
+    comps, og = po.loss_and_grad(z.numpy().astype(np.float64), t.numpy().astype(np.float64), po.STAGE2, 1)
+    assert rel_scalar(rep[0].item(), comps[0]) < TOL and rel_max(g.cpu().numpy(), og) < TOL
+    before = g.clone()
+    Fn.scale_gradient(g, torch.ones((), device=dev))
+    assert torch.equal(g, before)
+    Fn.scale_gradient(g, torch.tensor(-2.5, device=dev))
+    assert torch.equal(g, before * -2.5)
+    gb = before.bfloat16()
+    Fn.scale_gradient(gb, torch.tensor(3.0, device=dev))
+    assert torch.allclose(gb.float(), before.bfloat16().float() * 3.0, rtol=1e-2)
+
+
+def test_retained_graph_second_backward(dev, po):
+    """the eager gradient buffer is handed out once; a second backward recomputes from the saved sums"""
+    import physics_informed_image_segmentation_b200 as P
+
+    z, t = iid_inputs(2, 24, 32, seed=19)
+    crit = P.DiceBCEPDELoss(pde_weight=1e-4, phase_field_weight=1e-4, diffusion_coeff=5.0).to(dev)
+    x = z.to(dev).requires_grad_(True)
+    loss = crit.forward_logits(x, t.to(dev))
+    loss.backward(retain_graph=True)
+    g1 = x.grad.clone()
+    x.grad = None
+    (2.0 * loss).backward()
+    assert rel_max(x.grad.cpu().numpy(), 2.0 * g1.cpu().numpy()) < 2e-6
+    comps, og = po.loss_and_grad(z.numpy().astype(np.float64), t.numpy().astype(np.float64), po.STAGE2, 1)
+    assert rel_max(g1.cpu().numpy(), og) < TOL
