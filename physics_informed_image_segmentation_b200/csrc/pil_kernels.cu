@@ -34,8 +34,8 @@ constexpr int kOutLanes = 30;               // lanes of a warp that own output c
 constexpr int kStripCols = kOutLanes * kVec;  // 120 output columns per warp
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kFwdMinBlocks = 7;  // 32 warps / SM, <= 64 registers
-constexpr int kBwdMinBlocks = 4;  // 24 warps / SM, <= 85 registers
+constexpr int kFwdMinBlocks = 7;  // 28 warps / SM, <= 73 registers
+constexpr int kBwdMinBlocks = 4;  // 16 warps / SM, <= 128 registers (spilling at 5 blocks costs more than the occupancy gains)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kLogClampLog2 = -100.0f * kLog2e;  // nn.BCELoss clamps ln() at -100
