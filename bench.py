@@ -194,14 +194,31 @@ def run_ours(args):
     n_global = n_local * world
 
     sb = torch.empty(8, dtype=torch.float64, device=dev)
+    tot = torch.empty(8, dtype=torch.float64, device=dev)
 
-    def fwd_part():
+    # Data-parallel exchange of the 8-double sums vectors: "peer" = the kernels swap them themselves through
+    # peer-mapped mailboxes over NVLink (include/pil.h PilExchange; no collective call, 2 launches per
+    # step); "nccl" = all-reduce between the kernels (the baseline this replaces).
+    exchange = args.exchange if distributed else "none"
+    px = None
+    if exchange == "peer":
+        from physics_informed_image_segmentation_b200.sharding import PeerExchange
+
+        px = PeerExchange(dev)
+
+    def fwd_part(ex=None):
         """K1L: pointwise sums (I, P, T, BCE, double well), one flat pass over x and t."""
-        Fn.forward_pointwise(z, t, p, kind, sums=sums)
+        if ex is not None:
+            Fn.forward_pointwise_xchg(z, t, p, kind, ex, sums=sums)
+        else:
+            Fn.forward_pointwise(z, t, p, kind, sums=sums)
 
-    def bwd_part():
-        """[all-reduce of the 8 doubles] -> K2: gradient + the two stencil sums -> loss report."""
-        if distributed:
+    def bwd_part(ex=None):
+        """[exchange of the 8 doubles] -> K2: gradient + the two stencil sums -> loss report."""
+        if ex is not None:
+            Fn.backward_accumulate_xchg(z, t, p, kind, ex, n_global, grad_scale=float(world), out=grad, stencil_sums=sb,
+                                        report=report, total_sums=tot)
+        elif distributed:
             dist.all_reduce(sums)                                   # the gradient needs the global I, P, T
             Fn.backward_accumulate(z, t, p, kind, sums, n_global, grad_scale=float(world), out=grad, stencil_sums=sb)
             dist.all_reduce(sb)                                     # only the loss value needs these
@@ -209,14 +226,21 @@ def run_ours(args):
         else:
             Fn.backward_accumulate(z, t, p, kind, sums, n_global, out=grad, stencil_sums=sb, report=report)
 
+    def step():
+        ex = px.next_step() if px is not None else None
+        fwd_part(ex)
+        bwd_part(ex)
+
     for _ in range(max(args.warmup, 3)):
-        fwd_part()
-        bwd_part()
+        step()
     torch.cuda.synchronize()
     k0 = Fn.launch_info().kernels_launched
 
+    # ---- timed region 1 (the headline `value`): exactly K steps back to back, one event pair around them.
+    # The two kernels of a step are launched with programmatic dependent launch, so the next kernel's
+    # blocks fill the SMs while the previous one drains; nothing is recorded between them.
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -224,29 +248,40 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
+    e_beg.record()
     for k in range(K):
-        ev[k][0].record()
-        fwd_part()
-        ev[k][1].record()
-        bwd_part()
-        ev[k][2].record()
+        step()
+    e_end.record()
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
     wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
     info = Fn.launch_info()
     launches = info.kernels_launched - k0
+    total_ms = e_beg.elapsed_time(e_end)
 
-    total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
+    # ---- timed region 2 (roofline of the individual kernels): the same K steps with an event between the
+    # two kernels.  The clock sampler keeps running.
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    torch.cuda.synchronize()
+    for k in range(K):
+        ex = px.next_step() if px is not None else None
+        ev[k][0].record()
+        fwd_part(ex)
+        ev[k][1].record()
+        bwd_part(ex)
+        ev[k][2].record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     fwd_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
-    bwd_ms = [ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]  # multi-GPU: includes the all-reduce + finalize
+    bwd_ms = [ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]  # multi-GPU: includes the exchange wait
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms_max = float(tt.item())
     value = n_global * K / (total_ms_max * 1e-3) / 1e9
     loss_val = float(report[0].item())
+    xchg_timeout = bool(px.timed_out()) if px is not None else False
 
     # ---- end to end through the host-buffer C ABI --------------------------------------------------
     e2e = None
@@ -283,35 +318,48 @@ def run_ours(args):
         ach_b = bpp_b * n_local / (bwd_med * 1e-3) / 1e9
         ach_f = bpp_f * n_local / (fwd_med * 1e-3) / 1e9
         ach_step = (bpp_f + bpp_b) * n_local * K / (total_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of the backward kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("workload") == f"{name}_{'fp32' if args.dtype == 'f32' else 'bf16'}":
+                kb = tj["kernels"]["pil_bwd_kernel"]
+                traffic, traffic_src = kb["dram_bytes_read"] + kb["dram_bytes_write"], tj.get("source")
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{name}_{'fp32' if args.dtype == 'f32' else 'bf16'}", "per_gpu_batch": [B, 1, H, W],
                        "global_batch": B * world, "stage2_params": STAGE2, "entry": "logits (sigmoid fused)",
-                       "parallelism": f"dp{world} (batch shards; all-reduce of 8 doubles between the two kernels)",
+                       "parallelism": f"dp{world} (batch shards; exchange of 8 doubles between the two kernels: {exchange})",
                        "l2_policy": "inputs+gradient %.0f MB per step >> 126 MB L2, no flush needed" % (3 * n_local * esz / 1e6),
                        "step": "pil_forward_pointwise -> pil_backward_accumulate (stencils evaluated once per step)",
                        "tiling": {"fwd_blocks": info.fwd_blocks, "bwd_blocks": info.bwd_blocks,
                                   "bwd_rows_per_range": info.bwd_rows_per_segment}},
             "roofline": {"bound": "hbm", "kernel": "pil_bwd_kernel (gradient + stencil sums)", "achieved": ach_b, "peak": peak, "unit": "GB/s",
-                         "frac": ach_b / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach_b / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bpp_b * n_local, "kernel_ms": bwd_med,
-                         "note": "multi-GPU: bwd interval includes the sums all-reduce + finalize" if distributed else None},
+                         "note": "kernel_ms: median CUDA-event interval around the launch in a second pass over the same K steps; "
+                                 + ("multi-GPU: the interval includes the wait for the other ranks' sums" if distributed else "single GPU")},
             "roofline_fwd": {"kernel": "pil_point_kernel (pointwise sums)", "achieved": ach_f, "frac": ach_f / peak, "kernel_ms": fwd_med,
                              "algorithmic_bytes_per_launch": bpp_f * n_local},
             "roofline_step": {"achieved": ach_step, "frac": ach_step / peak, "bytes_per_pixel": bpp_f + bpp_b},
             "gpu_launches": int(launches), "clocks": clocks, "loss": loss_val, "wall_ms_per_step": 1e3 * wall / K,
+            "exchange_timeout": xchg_timeout,
         }
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
             sample_B = max(1, min(B, (8 * 1024 * 1024) // (H * W)))
-            px, times, cores = cpu_port_time(sample_B, H, W, iters=3, warm=1)
-            line["cpu_baseline"] = {"value": px / statistics.median(times) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            npx, times, cores = cpu_port_time(sample_B, H, W, iters=3, warm=1)
+            line["cpu_baseline"] = {"value": npx / statistics.median(times) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample_B}x1x{H}x{W} (of {B}x1x{H}x{W}), median of 3 after 1 warm-up, "
                                               f"torch {torch.__version__} CPU ops, op-for-op port of the reference loss"}
         print(json.dumps(line), flush=True)
+    if px is not None:
+        px.close()
     if distributed:
         dist.destroy_process_group()
 
@@ -324,6 +372,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg3")
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="multi-GPU: how the 8-double sums vectors cross ranks (peer-memory mailboxes | NCCL all-reduce)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

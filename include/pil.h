@@ -47,7 +47,8 @@ typedef enum PilStatus {
     PIL_ERR_THRESHOLD = -7,   /* reaction_threshold not in (0,1) (ValueError at src/pde.py:16-17) */
     PIL_ERR_EPSILON = -8,     /* epsilon <= 0 while phase_field_weight > 0 (src/pde.py:199-200) */
     PIL_ERR_ALIGNMENT = -9,   /* a pointer is not aligned to its element size */
-    PIL_ERR_SESSION = -10     /* session misuse (batch larger than created for, ...) */
+    PIL_ERR_SESSION = -10,    /* session misuse (batch larger than created for, ...) */
+    PIL_ERR_EXCHANGE = -11    /* bad PilExchange descriptor */
 } PilStatus;
 
 typedef enum PilDtype {
@@ -167,6 +168,58 @@ int pil_loss_fwd_bwd(const void* x, const void* t, void* grad, int64_t B, int64_
                      int x_dtype, int t_dtype, int x_kind, const PilParams* p,
                      double* sums, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
 int pil_scale_gradient(void* grad, int dtype, int64_t n, const float* upstream, void* stream);
+
+/*
+ * Data-parallel training step over PEER MEMORY (one process per GPU of one NVLink/NVSwitch node).
+ * The batch shards by whole images (every image has its own mirror boundary, src/pde.py:67, so no halo
+ * exchange); the only coupling is the batch-global reductions of src/loss.py:134-141 and
+ * src/pde.py:143,:210.  Instead of an NCCL all-reduce between the two kernels, the kernels exchange
+ * their 8-double vectors themselves: the last block of pil_forward_pointwise_xchg stores the shard's
+ * sums into every rank's mailbox (remote stores over NVLink + a release flag), every block of
+ * pil_backward_accumulate_xchg waits on its LOCAL copy of the flags and adds the vectors in rank order
+ * (bit-identical global sums on all ranks), and its last block swaps the stencil sums the same way
+ * and finalises the GLOBAL loss report.  Two launches per step, no collective call, no host sync.
+ *
+ * Set-up (host, once): every rank calls pil_exchange_alloc, the ranks exchange the 64-byte IPC
+ * handles out of band (torch.distributed / MPI / a file), and open each peer's with
+ * pil_exchange_open; mailbox[rank] is the rank's own pointer.  Per step all ranks pass the SAME
+ * `epoch`, incremented by one every step, and run the two calls in this order on one stream.
+ * Every rank must own its GPU: the kernels wait on flags written by kernels of other ranks.
+ * A wait that exceeds PIL_XCHG_TIMEOUT_MS (default 20000) gives up: the loss report becomes NaN and
+ * the mailbox status word (pil_exchange_status) is set.
+ */
+#define PIL_MAX_RANKS 8
+#define PIL_IPC_HANDLE_BYTES 64
+#define PIL_XCHG_DEFER_FINALIZE 1u /* the backward only pushes its stencil sums; pil_exchange_finalize assembles the loss */
+typedef struct PilExchange {
+    int32_t rank, world;
+    uint64_t epoch;
+    uint32_t flags, reserved;
+    void* mailbox[PIL_MAX_RANKS]; /* device pointers valid in THIS process: own mailbox and the opened peers */
+} PilExchange;
+size_t pil_exchange_bytes(void);
+int pil_exchange_alloc(void** mailbox, void* ipc_handle_out /* PIL_IPC_HANDLE_BYTES, may be NULL */);
+int pil_exchange_open(const void* ipc_handle, void** peer_mailbox);
+int pil_exchange_close(void* peer_mailbox);
+int pil_exchange_free(void* mailbox);
+int pil_exchange_status(const void* mailbox, int* status_out, void* stream); /* host sync; 0 = no timeout so far */
+int pil_forward_pointwise_xchg(const void* x, const void* t, int64_t B, int64_t H, int64_t W,
+                               int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                               double* sums /* this shard's */, void* workspace, size_t workspace_bytes,
+                               const PilExchange* ex, void* stream);
+/* grad of THIS shard from the GLOBAL sums; stencil_sums: this shard's; loss_out (PIL_NOUT floats) and
+ * total_sums (PIL_NSUMS doubles, may be NULL): the GLOBAL batch, identical on every rank. */
+int pil_backward_accumulate_xchg(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W,
+                                 int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                                 const PilExchange* ex, int64_t n_global, const float* upstream, float grad_scale,
+                                 double* stencil_sums, float* loss_out, double* total_sums,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+/* With PIL_XCHG_DEFER_FINALIZE the backward kernel does not wait for the other ranks' stencil sums;
+ * this one-thread kernel does, later on the stream (e.g. after the optimizer step was enqueued).
+ * It is also how several ranks are emulated on ONE GPU in the tests: there a kernel must never wait
+ * for a flag that a LATER launch writes, so all backwards are enqueued first, then the finalizes. */
+int pil_exchange_finalize(const PilExchange* ex, int64_t n_global, const PilParams* p,
+                          float* loss_out, double* total_sums, void* stream);
 
 /*
  * The PDERegularization operators a caller can use on their own (fp32 maps):

@@ -40,6 +40,18 @@ class PilLaunchInfo(ctypes.Structure):
         "bwd_blocks", "bwd_threads", "bwd_rows_per_segment", "bwd_aligned")] + [("kernels_launched", ctypes.c_int64)]
 
 
+PIL_MAX_RANKS = 8
+PIL_IPC_HANDLE_BYTES = 64
+PIL_XCHG_DEFER_FINALIZE = 1
+
+
+class PilExchange(ctypes.Structure):
+    """include/pil.h PilExchange: the peer-memory mailboxes of a data-parallel group."""
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("epoch", ctypes.c_uint64),
+                ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("mailbox", ctypes.c_void_p * PIL_MAX_RANKS)]
+
+
 class PilError(RuntimeError):
     def __init__(self, status: int, where: str):
         self.status = status
@@ -100,6 +112,23 @@ _SIGS = {
     "pil_loss_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PilParams),
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "pil_exchange_bytes": (ctypes.c_size_t, []),
+    "pil_exchange_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "pil_exchange_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "pil_exchange_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "pil_exchange_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "pil_exchange_status": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    "pil_exchange_finalize": (ctypes.c_int, [ctypes.POINTER(PilExchange), ctypes.c_int64, ctypes.POINTER(PilParams),
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pil_forward_pointwise_xchg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PilParams),
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                  ctypes.POINTER(PilExchange), ctypes.c_void_p]),
+    "pil_backward_accumulate_xchg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.POINTER(PilParams), ctypes.POINTER(PilExchange), ctypes.c_int64,
+                                                    ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "pil_scale_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "pil_laplacian": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_void_p]),

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "pil.h"
 
@@ -310,6 +311,18 @@ struct Geo {
     long long tasks;       // groups * strips warp-tasks
 };
 
+// peer-memory exchange descriptor handed to the kernels (see the exchange helpers below)
+constexpr int kSlotBytes = 128;  // 16 words of {32-bit payload half, 32-bit step tag}
+constexpr int kXchgStatusOffset = 2 * 2 * PIL_MAX_RANKS * kSlotBytes;  // int status word after the slots
+struct XchgDev {
+    int rank, world;             // world == 0: exchange disabled
+    int parity;
+    int defer;                   // PIL_XCHG_DEFER_FINALIZE: the backward only pushes phase 1
+    unsigned long long want;     // flag value of this step (epoch + 1)
+    unsigned long long timeout_ns;
+    unsigned char* box[PIL_MAX_RANKS];
+};
+
 struct FwdArgs {
     const void* x;
     const void* t;
@@ -340,6 +353,8 @@ struct BwdArgs {
     double* stencil_sums;  // out: {0,0,0,0, sum r^2, (eps/8) sum(dx^2+dy^2), 0, 0} of this shard
     float* loss_out;       // optional: finalize(gsums + stencil_sums) as if this shard were the batch
     double* total_sums;    // optional: gsums + stencil_sums (may alias gsums: written by the last block only)
+    XchgDev X;             // world > 0: global sums come from the mailbox (phase 0); the last block exchanges
+                           // the stencil sums (phase 1) and finalises the GLOBAL loss
 };
 
 __device__ __forceinline__ void finalize_device(const double* s, double n, const PilParams& p, float* out) {
@@ -361,6 +376,93 @@ __device__ __forceinline__ void finalize_device(const double* s, double n, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every hot kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its blocks may become resident while the
+// previous kernel of the stream is still draining (tail blocks, the last-block reduction, the launch
+// latency itself).  pdl_wait() blocks until the previous kernel has completed and its writes are
+// visible; nothing written by an earlier kernel may be touched before it.  pdl_launch_dependents()
+// lets the NEXT kernel's blocks be scheduled as soon as SM resources free up.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Peer-memory exchange of the sums vectors (data parallel, one process per GPU; include/pil.h
+// PilExchange).  Every rank owns a small mailbox in its own HBM that all peers have mapped (CUDA IPC
+// over NVLink/NVSwitch).  The last block of a kernel PUSHES its shard's 8 doubles into slot
+// [phase][epoch parity][my rank] of every rank's mailbox (16 remote 8-byte stores, each carrying its
+// own step tag); the consumer POLLS its own, local copy and adds the R vectors in rank order, so every
+// rank forms bit-identical global sums.  No NCCL call, no extra launch, no host involvement.
+//   phase 0: pointwise sums  (pushed by the pointwise forward, consumed by every block of the backward)
+//   phase 1: stencil sums    (pushed by the backward's last block, consumed by that same block)
+// Slot reuse: a slot of parity q is rewritten two steps later; by then every rank has passed the
+// phase-0 wait of the step in between, which is stream-ordered after its reads of the old value.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned char* xchg_slot(unsigned char* base, int phase, int parity, int src) {
+    return base + (size_t)(((phase * 2 + parity) * PIL_MAX_RANKS + src) * kSlotBytes);
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wire format ("LL" style, no fences): a slot is 16 words of 8 bytes, word w = {32-bit half w of the
+// 8 doubles, 32-bit step tag}.  A naturally aligned 8-byte store is single-copy atomic, so a reader that
+// sees the tag of this step in a word also sees that word's payload -- no release/acquire pair, no
+// system-scope fence (which would cost an NVLink round trip in the kernel's tail).
+constexpr int kSlotWords = 2 * PIL_NSUMS;
+static_assert(kSlotWords * 8 == kSlotBytes, "slot layout");
+
+// called by ALL threads of ONE block (blockDim >= 16*world): v (shared memory) -> every rank's mailbox
+__device__ __forceinline__ void xchg_push(const XchgDev& X, int phase, const double* v) {
+    const int i = (int)threadIdx.x;
+    if (i < kSlotWords * X.world) {
+        const int r = i / kSlotWords, w = i % kSlotWords;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v[w >> 1]);
+        const unsigned long long half = (w & 1) ? (bits >> 32) : (bits & 0xffffffffull);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(xchg_slot(X.box[r], phase, X.parity, X.rank)) + w;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(half | (X.want << 32)) : "memory");
+    }
+}
+// called by ALL threads of ONE block (blockDim >= 16*world; contains __syncthreads): waits for the R
+// vectors of `phase` in the LOCAL mailbox and adds them in rank order into out[0..7] (shared memory).
+// On timeout the sums are NaN and the mailbox status word is set.
+__device__ __noinline__ void xchg_wait_sum(const XchgDev& X, int phase, double* out) {
+    __shared__ unsigned int s_half[PIL_MAX_RANKS * kSlotWords];
+    __shared__ int s_bad;
+    const int i = (int)threadIdx.x;
+    if (i == 0) s_bad = 0;
+    __syncthreads();
+    if (i < kSlotWords * X.world) {
+        const int r = i / kSlotWords, w = i % kSlotWords;
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(xchg_slot(X.box[X.rank], phase, X.parity, r)) + w;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned long long word;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
+            if ((word >> 32) == X.want) break;
+            if (globaltimer_ns() - t0 > X.timeout_ns) {
+                s_bad = 1;
+                break;
+            }
+            __nanosleep(32);
+        }
+        s_half[i] = (unsigned int)(word & 0xffffffffull);
+    }
+    __syncthreads();
+    if (i < PIL_NSUMS) {
+        double v = 0.0;
+        for (int r = 0; r < X.world; ++r) {
+            const unsigned long long lo = s_half[r * kSlotWords + 2 * i], hi = s_half[r * kSlotWords + 2 * i + 1];
+            v += __longlong_as_double((long long)(lo | (hi << 32)));
+        }
+        out[i] = s_bad ? __longlong_as_double(0x7ff8000000000000LL) : v;
+    }
+    if (i == 0 && s_bad) *reinterpret_cast<volatile int*>(X.box[X.rank] + kXchgStatusOffset) = 1;
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Deterministic two-level reduction of the 8 per-thread accumulators:
 //   warp shuffles -> per-block doubles in `partials` -> the LAST block to finish (ticket) adds all
 //   per-block partials in a fixed order, so the result does not depend on block scheduling.
@@ -372,7 +474,8 @@ template <int THREADS>
 __device__ __forceinline__ bool reduce_to_last_block(const float* acc, double* partials, unsigned int* ticket, double* out) {
     constexpr int kWarps = THREADS / 32;
     __shared__ double s_part[kWarps][PIL_NSUMS];
-    __shared__ double s_red[THREADS];
+    __shared__ double s_red[2 * THREADS];
+    __shared__ double s_tot[PIL_NSUMS];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -399,32 +502,39 @@ __device__ __forceinline__ bool reduce_to_last_block(const float* acc, double* p
     if (!s_last) return false;
     __threadfence();
     {
-        // THREADS/8 row-groups x 8 components, 8 independent L2 loads in flight per thread, fixed order
-        constexpr int kGroups = THREADS / 8, kIlp = 8;
-        const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
+        // THREADS/4 block-groups x 4 component PAIRS: 16-byte L2 loads, 8 in flight per thread (the tail
+        // batch is predicated, not serialised), fixed order -> bit-reproducible.  This is serial time
+        // at the very end of the kernel, so it is kept to 2-3 L2 round trips.
+        constexpr int kGroups = THREADS / 4, kIlp = 8;
+        const int c2 = threadIdx.x & 3, j = threadIdx.x >> 2;
         const long long nb = gridDim.x;
-        double v = 0.0;
-        long long blk = j;
-        for (; blk + (kIlp - 1) * kGroups < nb; blk += kIlp * kGroups) {
-            double w[kIlp];
+        double vx = 0.0, vy = 0.0;
+        for (long long blk = j; blk < nb; blk += (long long)kIlp * kGroups) {
+            double2 w[kIlp];
 #pragma unroll
-            for (int q = 0; q < kIlp; ++q) w[q] = __ldcg(partials + (blk + q * kGroups) * PIL_NSUMS + c);
+            for (int q = 0; q < kIlp; ++q) {
+                const long long b = blk + (long long)q * kGroups;
+                w[q] = (b < nb) ? __ldcg(reinterpret_cast<const double2*>(partials + b * PIL_NSUMS) + c2) : make_double2(0.0, 0.0);
+            }
 #pragma unroll
-            for (int q = 0; q < kIlp; ++q) v += w[q];
+            for (int q = 0; q < kIlp; ++q) {
+                vx += w[q].x;
+                vy += w[q].y;
+            }
         }
-        for (; blk < nb; blk += kGroups) v += __ldcg(partials + blk * PIL_NSUMS + c);
-        s_red[threadIdx.x] = v;
+        s_red[2 * threadIdx.x] = vx;       // s_red viewed as [kGroups][8]
+        s_red[2 * threadIdx.x + 1] = vy;
     }
     __syncthreads();
     if (threadIdx.x < PIL_NSUMS) {
         double v = 0.0;
-        for (int j = 0; j < THREADS / 8; ++j) v += s_red[j * 8 + threadIdx.x];
-        s_red[threadIdx.x] = v;
+        for (int j = 0; j < THREADS / 4; ++j) v += s_red[j * 8 + threadIdx.x];
+        s_tot[threadIdx.x] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < PIL_NSUMS; ++k) out[k] = s_red[k];
+        for (int k = 0; k < PIL_NSUMS; ++k) out[k] = s_tot[k];
     }
     return true;
 }
@@ -775,10 +885,15 @@ struct PointArgs {
     unsigned int* ticket;
     double* sums;
     PilParams p;
+    XchgDev X;               // world > 0: the last block pushes the shard's sums to every rank (phase 0)
 };
 
 template <int KIND, typename XT, typename TT, bool ALIGNED>
 __global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const PointArgs A) {
+    // PDL: x and t may have been written by the kernel just before this one -> wait first; then let the
+    // backward kernel's blocks take the SM slots this grid frees as its blocks retire.
+    pdl_wait();
+    pdl_launch_dependents();
     FwdRow<KIND, true> fr;
 #pragma unroll
     for (int k = 0; k < 8; ++k) fr.acc[k] = 0.f;
@@ -837,12 +952,20 @@ __global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const Point
     }
     double raw[PIL_NSUMS];
     if (!reduce_to_last_block<kPointThreads>(fr.acc, A.partials, A.ticket, raw)) return;
+    __shared__ double s_push[PIL_NSUMS];
     if (threadIdx.x == 0) {
         double sv[PIL_NSUMS];
         sums_from_raw(raw, A.p.epsilon, (double)A.n, sv);
 #pragma unroll
-        for (int k = 0; k < PIL_NSUMS; ++k) A.sums[k] = sv[k];
+        for (int k = 0; k < PIL_NSUMS; ++k) {
+            A.sums[k] = sv[k];
+            s_push[k] = sv[k];
+        }
         *A.ticket = 0u;
+    }
+    if (A.X.world > 0) {  // data parallel: hand the shard's sums to every rank over NVLink
+        __syncthreads();
+        xchg_push(A.X, 0, s_push);
     }
 }
 
@@ -862,19 +985,37 @@ struct BwdCoef {
 
 // accumulate mode: reduce the stencil sums across the grid; the last block publishes them and,
 // if asked, assembles the loss from (global pointwise sums + these) -- src/loss.py:144-160.
-__device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const float* acc) {
+__device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const float* acc, const double* gs) {
     double raw[PIL_NSUMS];
     if (!reduce_to_last_block<kThreads>(acc, A.partials, A.ticket, raw)) return;
+    __shared__ double s_push[PIL_NSUMS];   // this shard's stencil sums
+    __shared__ double s_glob[PIL_NSUMS];   // the global stencil sums
     if (threadIdx.x == 0) {
         double sb[PIL_NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         sb[4] = raw[4];
         sb[5] = (A.p.epsilon / 8.0) * raw[5];
 #pragma unroll
-        for (int k = 0; k < PIL_NSUMS; ++k) A.stencil_sums[k] = sb[k];
-        if (A.loss_out != nullptr || A.total_sums != nullptr) {
+        for (int k = 0; k < PIL_NSUMS; ++k) {
+            A.stencil_sums[k] = sb[k];
+            s_push[k] = sb[k];
+            s_glob[k] = sb[k];
+        }
+    }
+    bool finalize = true;
+    if (A.X.world > 0) {  // data parallel: swap the stencil sums with every rank, then finalise globally
+        __syncthreads();
+        xchg_push(A.X, 1, s_push);
+        if (A.X.defer) {
+            finalize = false;
+        } else {
+            xchg_wait_sum(A.X, 1, s_glob);
+        }
+    }
+    if (threadIdx.x == 0) {
+        if ((A.loss_out != nullptr || A.total_sums != nullptr) && finalize) {
             double tot[PIL_NSUMS];
 #pragma unroll
-            for (int k = 0; k < PIL_NSUMS; ++k) tot[k] = A.gsums[k] + sb[k];
+            for (int k = 0; k < PIL_NSUMS; ++k) tot[k] = gs[k] + s_glob[k];
             if (A.loss_out != nullptr) finalize_device(tot, A.n_global > 0 ? (double)A.n_global : tot[7], A.p, A.loss_out);
             if (A.total_sums != nullptr) {  // every block has read gsums long before the last one gets here
 #pragma unroll
@@ -893,10 +1034,41 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
     // hit the part of x and t that the pointwise forward (a front-to-back stream) left in L2.
     const long long blk = A.reverse ? (long long)(gridDim.x - 1 - blockIdx.x) : (long long)blockIdx.x;
     const long long task = blk * kWarpsPerBlock + warp;
+
+    // ---- PDL prologue: nothing an earlier kernel wrote may be READ before pdl_wait(), but the rows this
+    // warp starts with can already be pulled into L2 (a prefetch has no architectural effect), so the
+    // DRAM latency of the pipeline fill overlaps the tail of the previous kernel.
+    if (task < g.tasks) {
+        const long long grp0 = task / g.strips;
+        const long long pos0 = (g.total_rows * grp0) / g.groups;
+        const int colp = min(max((int)(task % g.strips) * kStripCols + (lane - 1) * kVec, 0), g.W - 1);
+        if ((lane & 7) == 0 || lane == 31) {
+            const char* xp = reinterpret_cast<const char*>(A.x) + (pos0 * g.W + colp) * (long long)sizeof(XT);
+            const char* tp = reinterpret_cast<const char*>(A.t) + (pos0 * g.W + colp) * (long long)sizeof(TT);
+#pragma unroll
+            for (int q = -2; q < kStages; ++q) {
+                if (pos0 + q >= 0 && pos0 + q < g.total_rows) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + (long long)q * g.W * (long long)sizeof(XT)));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + (long long)q * g.W * (long long)sizeof(TT)));
+                }
+            }
+        }
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+
+    // ---- global sums: given, or (data parallel) collected from the peer mailbox -----------------
+    __shared__ double s_gs[PIL_NSUMS];
+    const double* gs = A.gsums;
+    if (A.X.world > 0) {
+        xchg_wait_sum(A.X, 0, s_gs);
+        gs = s_gs;
+    }
+
     if (task >= g.tasks) {
         if (A.accumulate) {  // idle warp of the last block still takes part in the block reduction
             const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            bwd_epilogue(A, zero);
+            bwd_epilogue(A, zero, gs);
         }
         return;
     }
@@ -904,11 +1076,11 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
     // ---- coefficients from the global sums (double once per thread, then fp32) -----------------
     BwdCoef c;
     {
-        const double I = A.gsums[0], P = A.gsums[1], T = A.gsums[2];
+        const double I = gs[0], P = gs[1], T = gs[2];
         const double s = A.p.smooth, den = P + T + s;
         double scale = (double)A.grad_scale * (A.upstream ? (double)__ldg(A.upstream) : 1.0);
         if (KIND == PIL_X_LOGITS_TANH) scale *= 2.0;  // d/dz sigmoid(2z) = 2 u (1-u)
-        const double invN = 1.0 / (A.n_global > 0 ? (double)A.n_global : A.gsums[7]);
+        const double invN = 1.0 / (A.n_global > 0 ? (double)A.n_global : gs[7]);
         const bool use_rd = A.p.pde_weight > 0.0, use_pf = A.p.phase_field_weight > 0.0;
         c.alpha = (float)(scale * A.p.dice_weight * (-2.0 / den));
         c.beta = (float)(scale * A.p.dice_weight * (2.0 * I + s) / (den * den));
@@ -1288,7 +1460,7 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         acc[4] = sr2s;
         acc[5] = sg2s;
     }
-    bwd_epilogue(A, acc);
+    bwd_epilogue(A, acc, gs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1303,6 +1475,23 @@ __global__ void pil_finalize_kernel(const double* sums, long long n_global, PilP
         double s[PIL_NSUMS];
         for (int k = 0; k < PIL_NSUMS; ++k) s[k] = sums[k];
         finalize_device(s, n_global > 0 ? (double)n_global : s[7], p, out);
+    }
+}
+
+// deferred finalisation of a data-parallel step: both exchanged vectors -> the global loss report
+__global__ void __launch_bounds__(kThreads) pil_xchg_finalize_kernel(XchgDev X, long long n_global, PilParams p, float* out, double* total_sums) {
+    __shared__ double s_a[PIL_NSUMS], s_b[PIL_NSUMS];
+    xchg_wait_sum(X, 0, s_a);
+    xchg_wait_sum(X, 1, s_b);
+    if (threadIdx.x == 0) {
+        double a[PIL_NSUMS];
+#pragma unroll
+        for (int k = 0; k < PIL_NSUMS; ++k) a[k] = s_a[k] + s_b[k];
+        if (out != nullptr) finalize_device(a, n_global > 0 ? (double)n_global : a[7], p, out);
+        if (total_sums != nullptr) {
+#pragma unroll
+            for (int k = 0; k < PIL_NSUMS; ++k) total_sums[k] = a[k];
+        }
     }
 }
 
@@ -1460,6 +1649,56 @@ static int tuning_waves(bool bwd, int64_t B, int64_t H, int64_t W, int resident_
     return w < 1 ? 1 : w;
 }
 
+// Launch with programmatic stream serialization (see pdl_wait above).  PIL_PDL=0 turns it off.
+static bool use_pdl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PIL_PDL");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+template <typename K, typename A>
+static cudaError_t launch_pdl(K kernel, int blocks, int threads, int smem, cudaStream_t s, const A& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
+static unsigned long long xchg_timeout_ns() {
+    static unsigned long long v = 0;
+    if (v == 0) {
+        const char* e = getenv("PIL_XCHG_TIMEOUT_MS");
+        const long long ms = (e && atoll(e) > 0) ? atoll(e) : 20000;
+        v = (unsigned long long)ms * 1000000ull;
+    }
+    return v;
+}
+static int make_xchg(const PilExchange* ex, XchgDev* X) {
+    *X = XchgDev{};
+    if (!ex) return PIL_OK;
+    if (ex->world < 1 || ex->world > PIL_MAX_RANKS || ex->rank < 0 || ex->rank >= ex->world) return PIL_ERR_EXCHANGE;
+    X->rank = ex->rank;
+    X->world = ex->world;
+    X->parity = (int)(ex->epoch & 1ull);
+    X->defer = (ex->flags & PIL_XCHG_DEFER_FINALIZE) ? 1 : 0;
+    X->want = (ex->epoch % 0xfffffffeull) + 1ull;  // 32-bit step tag, never 0 (mailboxes start zeroed)
+    X->timeout_ns = xchg_timeout_ns();
+    for (int r = 0; r < ex->world; ++r) {
+        if (!ex->mailbox[r]) return PIL_ERR_EXCHANGE;
+        X->box[r] = reinterpret_cast<unsigned char*>(ex->mailbox[r]);
+    }
+    return PIL_OK;
+}
+
 template <int KIND, typename XT, typename TT>
 static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned, size_t partial_bytes_avail,
                                 cudaStream_t s, LaunchOut* out) {
@@ -1487,16 +1726,25 @@ static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, boo
 #define PIL_FWD_PASS a, B, H, W, aligned, avail, s, out
 template <int KIND, typename XT>
 static cudaError_t launch_fwd_t(int t_dtype, PIL_FWD_ARGS) {
+#ifdef PIL_DEV_F32_ONLY  // development builds: fp32 maps only (6x faster to compile)
+    if (t_dtype != PIL_F32) return cudaErrorNotSupported;
+    return launch_fwd_a<KIND, XT, float>(PIL_FWD_PASS);
+#else
     switch (t_dtype) {
         case PIL_F32: return launch_fwd_a<KIND, XT, float>(PIL_FWD_PASS);
         case PIL_BF16: return launch_fwd_a<KIND, XT, __nv_bfloat16>(PIL_FWD_PASS);
         default: return launch_fwd_a<KIND, XT, uint8_t>(PIL_FWD_PASS);
     }
+#endif
 }
 template <int KIND>
 static cudaError_t launch_fwd_x(int x_dtype, int t_dtype, PIL_FWD_ARGS) {
     if (x_dtype == PIL_F32) return launch_fwd_t<KIND, float>(t_dtype, PIL_FWD_PASS);
+#ifdef PIL_DEV_F32_ONLY
+    return cudaErrorNotSupported;
+#else
     return launch_fwd_t<KIND, __nv_bfloat16>(t_dtype, PIL_FWD_PASS);
+#endif
 }
 
 template <int KIND, typename XT, typename TT>
@@ -1511,8 +1759,7 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
         a.g = make_geo(B, H, W, sm_count() * per_sm, g_tune_bwd_rps, tuning_waves(true, B, H, W, sm_count() * per_sm));
         out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
         out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
-        kernel<<<out->blocks, kThreads, smem, s>>>(a);
-        return cudaGetLastError();
+        return launch_pdl(kernel, out->blocks, kThreads, smem, s, a);
     };
     if (aligned) return go(pil_bwd_kernel<KIND, XT, TT, true>, kSmemPerBlock);
     return go(pil_bwd_kernel<KIND, XT, TT, false>, 0);
@@ -1521,16 +1768,25 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
 #define PIL_BWD_PASS a, B, H, W, aligned, s, out
 template <int KIND, typename XT>
 static cudaError_t launch_bwd_t(int t_dtype, PIL_BWD_ARGS) {
+#ifdef PIL_DEV_F32_ONLY  // development builds: fp32 maps only (6x faster to compile)
+    if (t_dtype != PIL_F32) return cudaErrorNotSupported;
+    return launch_bwd_a<KIND, XT, float>(PIL_BWD_PASS);
+#else
     switch (t_dtype) {
         case PIL_F32: return launch_bwd_a<KIND, XT, float>(PIL_BWD_PASS);
         case PIL_BF16: return launch_bwd_a<KIND, XT, __nv_bfloat16>(PIL_BWD_PASS);
         default: return launch_bwd_a<KIND, XT, uint8_t>(PIL_BWD_PASS);
     }
+#endif
 }
 template <int KIND>
 static cudaError_t launch_bwd_x(int x_dtype, int t_dtype, PIL_BWD_ARGS) {
     if (x_dtype == PIL_F32) return launch_bwd_t<KIND, float>(t_dtype, PIL_BWD_PASS);
+#ifdef PIL_DEV_F32_ONLY
+    return cudaErrorNotSupported;
+#else
     return launch_bwd_t<KIND, __nv_bfloat16>(t_dtype, PIL_BWD_PASS);
+#endif
 }
 
 template <int KIND, typename XT, typename TT>
@@ -1550,24 +1806,32 @@ static cudaError_t launch_point_a(const PointArgs& a, bool aligned, cudaStream_t
         if (blocks > kMaxPointBlocks) blocks = kMaxPointBlocks;
         if (blocks < 1) blocks = 1;
         *blocks_out = (int)blocks;
-        kernel<<<(int)blocks, kPointThreads, 0, s>>>(a);
-        return cudaGetLastError();
+        return launch_pdl(kernel, (int)blocks, kPointThreads, 0, s, a);
     };
     if (aligned) return go(pil_point_kernel<KIND, XT, TT, true>);
     return go(pil_point_kernel<KIND, XT, TT, false>);
 }
 template <int KIND, typename XT>
 static cudaError_t launch_point_t(int t_dtype, const PointArgs& a, bool aligned, cudaStream_t s, int* b) {
+#ifdef PIL_DEV_F32_ONLY  // development builds: fp32 maps only (6x faster to compile)
+    if (t_dtype != PIL_F32) return cudaErrorNotSupported;
+    return launch_point_a<KIND, XT, float>(a, aligned, s, b);
+#else
     switch (t_dtype) {
         case PIL_F32: return launch_point_a<KIND, XT, float>(a, aligned, s, b);
         case PIL_BF16: return launch_point_a<KIND, XT, __nv_bfloat16>(a, aligned, s, b);
         default: return launch_point_a<KIND, XT, uint8_t>(a, aligned, s, b);
     }
+#endif
 }
 template <int KIND>
 static cudaError_t launch_point_x(int x_dtype, int t_dtype, const PointArgs& a, bool aligned, cudaStream_t s, int* b) {
     if (x_dtype == PIL_F32) return launch_point_t<KIND, float>(t_dtype, a, aligned, s, b);
+#ifdef PIL_DEV_F32_ONLY
+    return cudaErrorNotSupported;
+#else
     return launch_point_t<KIND, __nv_bfloat16>(t_dtype, a, aligned, s, b);
+#endif
 }
 
 __global__ void __launch_bounds__(256) pil_scale_kernel(float* __restrict__ g, long long n4, const float* __restrict__ up) {
@@ -1630,6 +1894,7 @@ const char* pil_status_string(int status) {
         case PIL_ERR_EPSILON: return "epsilon must be positive";
         case PIL_ERR_ALIGNMENT: return "pointer not aligned to its element size";
         case PIL_ERR_SESSION: return "session misuse";
+        case PIL_ERR_EXCHANGE: return "bad PilExchange (rank/world out of range or a mailbox pointer is NULL)";
         default: break;
     }
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
@@ -1704,10 +1969,10 @@ int pil_finalize(const double* sums, int64_t n_global, const PilParams* p, float
 static int backward_impl(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
                          int x_kind, const PilParams* p, const double* global_sums, int64_t n_global, const float* upstream,
                          float grad_scale, double* stencil_sums, float* loss_out, double* total_sums, void* acc_ws,
-                         void* stream) {
+                         void* stream, const PilExchange* ex = nullptr) {
     int st = check_common(x, t, B, H, W, x_dtype, t_dtype, x_kind, p);
     if (st != PIL_OK) return st;
-    if (!grad || !global_sums) return PIL_ERR_NULL;
+    if (!grad || (!global_sums && !ex)) return PIL_ERR_NULL;
     if ((uintptr_t)grad % dtype_size(x_dtype)) return PIL_ERR_ALIGNMENT;
 
     BwdArgs a;
@@ -1733,6 +1998,8 @@ static int backward_impl(const void* x, const void* t, void* grad, int64_t B, in
     a.stencil_sums = stencil_sums;
     a.loss_out = loss_out;
     a.total_sums = total_sums;
+    st = make_xchg(ex, &a.X);
+    if (st != PIL_OK) return st;
     if (a.accumulate) {
         const WorkspaceLayout wl = workspace_layout(B, H, W);
         a.ticket = reinterpret_cast<unsigned int*>((char*)acc_ws + wl.ticket_off);
@@ -1776,9 +2043,9 @@ int pil_backward_accumulate(const void* x, const void* t, void* grad, int64_t B,
                          stencil_sums, loss_out, nullptr, workspace, stream);
 }
 
-int pil_forward_pointwise(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+static int pointwise_impl(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
                           int x_kind, const PilParams* p, double* sums, void* workspace, size_t workspace_bytes,
-                          void* stream) {
+                          void* stream, const PilExchange* ex) {
     int st = check_common(x, t, B, H, W, x_dtype, t_dtype, x_kind, p);
     if (st != PIL_OK) return st;
     if (!sums || !workspace) return PIL_ERR_NULL;
@@ -1792,6 +2059,8 @@ int pil_forward_pointwise(const void* x, const void* t, int64_t B, int64_t H, in
     a.partials = reinterpret_cast<double*>((char*)workspace + wl.partials_off);
     a.sums = sums;
     a.p = *p;
+    st = make_xchg(ex, &a.X);
+    if (st != PIL_OK) return st;
     // flat stream: only total size and base alignment matter
     const bool aligned = (a.n % 4 == 0) && is_aligned_case(x, t, nullptr, 4, x_dtype, t_dtype);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1808,6 +2077,88 @@ int pil_forward_pointwise(const void* x, const void* t, int64_t B, int64_t H, in
     t_info.fwd_aligned = aligned ? 1 : 0;
     ++g_kernels_launched;
     return (int)e;
+}
+
+int pil_forward_pointwise(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                          int x_kind, const PilParams* p, double* sums, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    return pointwise_impl(x, t, B, H, W, x_dtype, t_dtype, x_kind, p, sums, workspace, workspace_bytes, stream, nullptr);
+}
+
+// ---- data-parallel training step over the peer-memory exchange (no NCCL call, 2 launches) --------
+size_t pil_exchange_bytes(void) { return (size_t)kXchgStatusOffset + 128; }
+
+int pil_exchange_alloc(void** mailbox, void* ipc_handle_out) {
+    if (!mailbox) return PIL_ERR_NULL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == PIL_IPC_HANDLE_BYTES, "ipc handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, pil_exchange_bytes());
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(p, 0, pil_exchange_bytes());
+    if (e == cudaSuccess && ipc_handle_out) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle_out), p);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return (int)e;
+    }
+    *mailbox = p;
+    return PIL_OK;
+}
+
+int pil_exchange_open(const void* ipc_handle, void** peer_mailbox) {
+    if (!ipc_handle || !peer_mailbox) return PIL_ERR_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int pil_exchange_close(void* peer_mailbox) {
+    if (!peer_mailbox) return PIL_ERR_NULL;
+    return (int)cudaIpcCloseMemHandle(peer_mailbox);
+}
+
+int pil_exchange_free(void* mailbox) {
+    if (!mailbox) return PIL_ERR_NULL;
+    return (int)cudaFree(mailbox);
+}
+
+int pil_exchange_status(const void* mailbox, int* status_out, void* stream) {
+    if (!mailbox || !status_out) return PIL_ERR_NULL;
+    cudaError_t e = cudaMemcpyAsync(status_out, (const char*)mailbox + kXchgStatusOffset, sizeof(int), cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    return (int)e;
+}
+
+int pil_forward_pointwise_xchg(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                               int x_kind, const PilParams* p, double* sums, void* workspace, size_t workspace_bytes,
+                               const PilExchange* ex, void* stream) {
+    if (!ex) return PIL_ERR_NULL;
+    return pointwise_impl(x, t, B, H, W, x_dtype, t_dtype, x_kind, p, sums, workspace, workspace_bytes, stream, ex);
+}
+
+int pil_backward_accumulate_xchg(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype,
+                                 int t_dtype, int x_kind, const PilParams* p, const PilExchange* ex, int64_t n_global,
+                                 const float* upstream, float grad_scale, double* stencil_sums, float* loss_out,
+                                 double* total_sums, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!ex || !stencil_sums || !workspace) return PIL_ERR_NULL;
+    if (B >= 1 && H >= 2 && W >= 2) {
+        const WorkspaceLayout wl = workspace_layout(B, H, W);
+        if (workspace_bytes < wl.total || ((uintptr_t)workspace % 8)) return PIL_ERR_WORKSPACE;
+    }
+    return backward_impl(x, t, grad, B, H, W, x_dtype, t_dtype, x_kind, p, nullptr, n_global, upstream, grad_scale,
+                         stencil_sums, loss_out, total_sums, workspace, stream, ex);
+}
+
+int pil_exchange_finalize(const PilExchange* ex, int64_t n_global, const PilParams* p, float* loss_out, double* total_sums,
+                          void* stream) {
+    if (!ex || !p || (!loss_out && !total_sums)) return PIL_ERR_NULL;
+    XchgDev X;
+    int st = make_xchg(ex, &X);
+    if (st != PIL_OK) return st;
+    pil_xchg_finalize_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(X, (long long)n_global, *p, loss_out, total_sums);
+    ++g_kernels_launched;
+    return (int)cudaGetLastError();
 }
 
 int pil_loss_fwd_bwd(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,

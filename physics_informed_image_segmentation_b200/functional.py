@@ -228,6 +228,71 @@ def backward_accumulate(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: i
     return out, stencil_sums
 
 
+def forward_pointwise_xchg(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, ex: "_lib.PilExchange",
+                           sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1L + push of the shard's sums into every rank's mailbox (include/pil.h pil_forward_pointwise_xchg)."""
+    B, H, W = check_maps(x, t)
+    dev = x.device
+    if sums is None:
+        sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    ws = workspace(dev, B, H, W)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_forward_pointwise_xchg(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                                                   ctypes.byref(cp), sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                   ctypes.byref(ex), _stream_ptr(dev))
+    _lib.check(st, "pil_forward_pointwise_xchg")
+    return sums
+
+
+def backward_accumulate_xchg(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, ex: "_lib.PilExchange",
+                             n_global: int = -1, upstream: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                             out: Optional[torch.Tensor] = None, stencil_sums: Optional[torch.Tensor] = None,
+                             report: Optional[torch.Tensor] = None, total_sums: Optional[torch.Tensor] = None):
+    """K2 fed from the mailbox; its last block swaps the stencil sums and finalises the GLOBAL loss.
+    Returns (grad of this shard, report float32[8] of the global batch, total_sums float64[8])."""
+    B, H, W = check_maps(x, t)
+    dev = x.device
+    if out is None:
+        out = torch.empty_like(x)
+    if stencil_sums is None:
+        stencil_sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    if report is None:
+        report = torch.empty(PIL_NOUT, dtype=torch.float32, device=dev)
+    if total_sums is None:
+        total_sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    up_ptr = None
+    if upstream is not None:
+        if upstream.dtype != torch.float32 or upstream.numel() != 1 or upstream.device != dev:
+            upstream = upstream.to(device=dev, dtype=torch.float32).reshape(1)
+        up_ptr = upstream.data_ptr()
+    ws = workspace(dev, B, H, W)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_backward_accumulate_xchg(x.data_ptr(), t.data_ptr(), out.data_ptr(), B, H, W, _x_dtype(x),
+                                                     _t_dtype(t), kind, ctypes.byref(cp), ctypes.byref(ex), int(n_global),
+                                                     up_ptr, float(grad_scale), stencil_sums.data_ptr(), report.data_ptr(),
+                                                     total_sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(st, "pil_backward_accumulate_xchg")
+    return out, report, total_sums
+
+
+def exchange_finalize(ex: "_lib.PilExchange", n_global: int, p: LossParams, device: torch.device,
+                      report: Optional[torch.Tensor] = None, total_sums: Optional[torch.Tensor] = None):
+    """Deferred finalisation (PIL_XCHG_DEFER_FINALIZE): global report + complete global sums from the mailbox."""
+    dev = torch.device(device)
+    if report is None:
+        report = torch.empty(PIL_NOUT, dtype=torch.float32, device=dev)
+    if total_sums is None:
+        total_sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_exchange_finalize(ctypes.byref(ex), int(n_global), ctypes.byref(cp), report.data_ptr(),
+                                              total_sums.data_ptr(), _stream_ptr(dev))
+    _lib.check(st, "pil_exchange_finalize")
+    return report, total_sums
+
+
 def loss_fwd_bwd(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, grad: Optional[torch.Tensor] = None,
                  sums: Optional[torch.Tensor] = None, report: Optional[torch.Tensor] = None):
     """One training-step evaluation on a single shard: pointwise forward -> backward (+ stencil sums).
@@ -301,6 +366,19 @@ class _FusedLossFn(torch.autograd.Function):
             import torch.distributed as dist
 
             scale = float(dist.get_world_size(group)) if ddp_average else 1.0
+            from .sharding import peer_exchange_for
+
+            px = peer_exchange_for(group, x_d.device)
+            if px is not None and pg is p:
+                # peer-memory path: the two kernels swap their sums over NVLink themselves (no NCCL call)
+                ex = px.next_step()
+                forward_pointwise_xchg(x_d, t_d, pg, kind, ex)
+                grad, report, sums = backward_accumulate_xchg(x_d, t_d, pg, kind, ex, -1, grad_scale=scale)
+                ctx.save_for_backward(x_d, t_d, sums)
+                ctx.grad = grad
+                ctx.p, ctx.kind, ctx.n_global, ctx.scale = pg, kind, -1, scale
+                ctx.mark_non_differentiable(report)
+                return report[which], report
             sums = forward_pointwise(x_d, t_d, pg, kind)
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)           # the gradient needs global I, P, T
             grad, stencil = backward_accumulate(x_d, t_d, pg, kind, sums, -1, grad_scale=scale)

@@ -37,6 +37,119 @@ def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
     return sums
 
 
+class PeerExchange:
+    """Peer-memory mailboxes of one data-parallel group (include/pil.h PilExchange).
+
+    One process per GPU of one NVLink/NVSwitch node.  Construction allocates this rank's mailbox,
+    all-gathers the CUDA IPC handles through torch.distributed (plumbing) and maps every peer's
+    mailbox.  `next_step()` returns the descriptor for the next training step (epoch + 1): all
+    ranks must call it in lock step, which a data-parallel loop does by construction.
+    """
+
+    def __init__(self, device: torch.device, group=None):
+        import ctypes
+
+        import torch.distributed as dist
+
+        from . import _lib
+
+        L = _lib.lib()
+        self._lib = L
+        self.device = torch.device(device)
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > _lib.PIL_MAX_RANKS:
+            raise ValueError(f"peer exchange supports up to {_lib.PIL_MAX_RANKS} ranks, got {self.world}")
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * _lib.PIL_IPC_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            _lib.check(L.pil_exchange_alloc(ctypes.byref(own), handle), "pil_exchange_alloc")
+        self._own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._peers = {}
+        self._ex = _lib.PilExchange()
+        self._ex.rank, self._ex.world, self._ex.epoch = self.rank, self.world, 0
+        for r in range(self.world):
+            if r == self.rank:
+                self._ex.mailbox[r] = self._own
+                continue
+            ptr = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * _lib.PIL_IPC_HANDLE_BYTES).from_buffer_copy(handles[r])
+            with torch.cuda.device(self.device):
+                _lib.check(L.pil_exchange_open(buf, ctypes.byref(ptr)), "pil_exchange_open")
+            self._peers[r] = ptr.value
+            self._ex.mailbox[r] = ptr.value
+        self._epoch = 0
+        dist.barrier(group=group)  # nobody pushes before every mailbox is mapped everywhere
+
+    def next_step(self):
+        """Descriptor of the next step; the caller runs forward_pointwise_xchg then backward_accumulate_xchg with it."""
+        from . import _lib
+
+        ex = _lib.PilExchange()
+        ex.rank, ex.world, ex.epoch = self.rank, self.world, self._epoch
+        for r in range(self.world):
+            ex.mailbox[r] = self._ex.mailbox[r]
+        self._epoch += 1
+        return ex
+
+    def timed_out(self) -> bool:
+        """Host sync: has any exchange wait on this rank given up (peer dead / not in lock step)?"""
+        import ctypes
+
+        st = ctypes.c_int(0)
+        from . import _lib
+
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pil_exchange_status(self._own, ctypes.byref(st),
+                                                     torch.cuda.current_stream(self.device).cuda_stream), "pil_exchange_status")
+        return st.value != 0
+
+    def close(self):
+        import torch.distributed as dist
+
+        if self._own is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)  # no peer may still be writing into a mailbox that goes away
+            for ptr in self._peers.values():
+                self._lib.pil_exchange_close(ptr)
+            self._lib.pil_exchange_free(self._own)
+        self._peers, self._own = {}, None
+
+
+_EXCHANGES = {}
+
+
+def _group_key(group, device) -> tuple:
+    import torch.distributed as dist
+
+    g = None if (group is None or group is dist.group.WORLD) else group
+    return (id(g) if g is not None else 0, torch.device(device).index)
+
+
+def enable_peer_exchange(device: torch.device, group=None) -> PeerExchange:
+    """Collective: create (once) the peer-memory exchange the fused loss uses for `group`."""
+    key = _group_key(group, device)
+    if key not in _EXCHANGES:
+        _EXCHANGES[key] = PeerExchange(device, group)
+    return _EXCHANGES[key]
+
+
+def peer_exchange_for(group, device: torch.device) -> Optional[PeerExchange]:
+    return _EXCHANGES.get(_group_key(group, device))
+
+
+def disable_peer_exchange() -> None:
+    for px in list(_EXCHANGES.values()):
+        px.close()
+    _EXCHANGES.clear()
+
+
 def loss_report_from_sums(sums: Sequence[float], n_global: Optional[int], p: LossParams) -> dict:
     """Host-side assembly of the scalar loss from (all-reduced) sums -- the same arithmetic as the
     device finalize (reference src/loss.py:134-160), for logging and for tests that have no GPU."""
