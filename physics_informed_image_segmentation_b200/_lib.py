@@ -155,12 +155,16 @@ def lib() -> ctypes.CDLL:
     """The loaded library; builds it first when sources are newer and nvcc is available."""
     global _lib
     if _lib is None:
-        try:
-            build()
-        except RuntimeError:
-            if not os.path.exists(SO_PATH):
-                raise
-        L = ctypes.CDLL(SO_PATH)
+        override = os.environ.get("PIL_LIB")  # development: an instrumented build of the same sources
+        if override:
+            L = ctypes.CDLL(override)
+        else:
+            try:
+                build()
+            except RuntimeError:
+                if not os.path.exists(SO_PATH):
+                    raise
+            L = ctypes.CDLL(SO_PATH)
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)  # AttributeError here == the library does not export what pil.h declares
             fn.restype = res

@@ -353,6 +353,10 @@ struct BwdArgs {
     double* stencil_sums;  // out: {0,0,0,0, sum r^2, (eps/8) sum(dx^2+dy^2), 0, 0} of this shard
     float* loss_out;       // optional: finalize(gsums + stencil_sums) as if this shard were the batch
     double* total_sums;    // optional: gsums + stencil_sums (may alias gsums: written by the last block only)
+    // dynamic work distribution (accumulate mode): after its first, statically assigned range a warp
+    // claims further (range, strip) tasks from this counter; tasks [0, first_dynamic) are the static ones
+    unsigned int* task_counter;
+    long long first_dynamic;
     XchgDev X;             // world > 0: global sums come from the mailbox (phase 0); the last block exchanges
                            // the stencil sums (phase 1) and finalises the GLOBAL loss
 };
@@ -385,6 +389,27 @@ __device__ __forceinline__ void finalize_device(const double* s, double n, const
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Development instrumentation (-DPIL_TIMELINE, tools/timeline.py): per-block globaltimer stamps.
+#ifdef PIL_TIMELINE
+__device__ unsigned long long* g_timeline = nullptr;  // [kernel 0/1][4096 blocks][8]
+__device__ __forceinline__ void tl_stamp(int kernel, int slot) {
+    if (g_timeline != nullptr && threadIdx.x == 0 && blockIdx.x < 4096) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        unsigned long long* p = g_timeline + ((size_t)kernel * 4096 + blockIdx.x) * 8;
+        p[slot] = t;
+        if (slot == 0) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p[7] = smid;
+        }
+    }
+}
+#define TL_STAMP(k, s) tl_stamp(k, s)
+#else
+#define TL_STAMP(k, s)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Peer-memory exchange of the sums vectors (data parallel, one process per GPU; include/pil.h
@@ -470,8 +495,8 @@ __device__ __noinline__ void xchg_wait_sum(const XchgDev& X, int phase, double* 
 // *ticket to 0 when it is done (so the workspace is reusable by the next launch on the stream).
 // accumulator layout: 0 I, 1 P, 2 T, 3 bce (log2 units, un-negated), 4 r^2, 5 dx^2+dy^2, 6 (uv)^2, 7 #invalid
 // ------------------------------------------------------------------------------------------------
-template <int THREADS>
-__device__ __forceinline__ bool reduce_to_last_block(const float* acc, double* partials, unsigned int* ticket, double* out) {
+template <int THREADS, typename AccT>
+__device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* partials, unsigned int* ticket, double* out) {
     constexpr int kWarps = THREADS / 32;
     __shared__ double s_part[kWarps][PIL_NSUMS];
     __shared__ double s_red[2 * THREADS];
@@ -480,7 +505,7 @@ __device__ __forceinline__ bool reduce_to_last_block(const float* acc, double* p
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        float v = acc[k];
+        AccT v = acc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) s_part[warp][k] = (double)v;
@@ -855,7 +880,7 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
 
     // ---- deterministic cross-block reduction; the last block finalises --------------------------
     double raw[PIL_NSUMS];
-    if (!reduce_to_last_block<kThreads>(fr.acc, A.partials, A.ticket, raw)) return;
+    if (!reduce_to_last_block<kThreads, float>(fr.acc, A.partials, A.ticket, raw)) return;
     if (threadIdx.x == 0) {
         double s[PIL_NSUMS];
         sums_from_raw(raw, A.p.epsilon, (double)g.B * (double)g.H * (double)g.W, s);
@@ -892,8 +917,10 @@ template <int KIND, typename XT, typename TT, bool ALIGNED>
 __global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const PointArgs A) {
     // PDL: x and t may have been written by the kernel just before this one -> wait first; then let the
     // backward kernel's blocks take the SM slots this grid frees as its blocks retire.
+    TL_STAMP(0, 0);
     pdl_wait();
     pdl_launch_dependents();
+    TL_STAMP(0, 1);
     FwdRow<KIND, true> fr;
 #pragma unroll
     for (int k = 0; k < 8; ++k) fr.acc[k] = 0.f;
@@ -950,8 +977,12 @@ __global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const Point
             fr.acc[7] += 0.5f * one.acc[7];
         }
     }
+    TL_STAMP(0, 2);
     double raw[PIL_NSUMS];
-    if (!reduce_to_last_block<kPointThreads>(fr.acc, A.partials, A.ticket, raw)) return;
+    if (!reduce_to_last_block<kPointThreads, float>(fr.acc, A.partials, A.ticket, raw)) {
+        TL_STAMP(0, 3);
+        return;
+    }
     __shared__ double s_push[PIL_NSUMS];
     if (threadIdx.x == 0) {
         double sv[PIL_NSUMS];
@@ -967,6 +998,7 @@ __global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const Point
         __syncthreads();
         xchg_push(A.X, 0, s_push);
     }
+    TL_STAMP(0, 3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -981,13 +1013,17 @@ struct BwdCoef {
     float cW;            // pf  : cW * uv*(1-2u),   cW = scale*lpf/N*2/eps
     float D;
     float a1, c0;        // r = u*(u*(a1 - u) + c0) + D*(sum of 4 neighbours),  a1 = 1+a, c0 = -a - 4D
+    // packed path only
+    float beta_half;     // beta / 2 (travels with the horizontal transposed-stencil terms)
+    float f1c;           // f1 - 4 cA  (centre tap of the transposed Laplacian folded into f')
+    float cW2n;          // -2 cW       (cW uv (1-2u) = uv (cW2n u + cW))
 };
 
 // accumulate mode: reduce the stencil sums across the grid; the last block publishes them and,
 // if asked, assembles the loss from (global pointwise sums + these) -- src/loss.py:144-160.
-__device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const float* acc, const double* gs) {
+__device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const double* acc, const double* gs) {
     double raw[PIL_NSUMS];
-    if (!reduce_to_last_block<kThreads>(acc, A.partials, A.ticket, raw)) return;
+    if (!reduce_to_last_block<kThreads, double>(acc, A.partials, A.ticket, raw)) return;
     __shared__ double s_push[PIL_NSUMS];   // this shard's stencil sums
     __shared__ double s_glob[PIL_NSUMS];   // the global stencil sums
     if (threadIdx.x == 0) {
@@ -1022,6 +1058,7 @@ __device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const float* acc, co
                 for (int k = 0; k < PIL_NSUMS; ++k) A.total_sums[k] = tot[k];
             }
         }
+        if (A.task_counter != nullptr) *A.task_counter = 0u;  // every warp has made its last claim
         *A.ticket = 0u;
     }
 }
@@ -1030,32 +1067,47 @@ template <int KIND, typename XT, typename TT, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const BwdArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Geo& g = A.g;
-    // Blocks are dispatched in index order; walking the shard from its END first lets the first wave
-    // hit the part of x and t that the pointwise forward (a front-to-back stream) left in L2.
-    const long long blk = A.reverse ? (long long)(gridDim.x - 1 - blockIdx.x) : (long long)blockIdx.x;
-    const long long task = blk * kWarpsPerBlock + warp;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    TL_STAMP(1, 0);
 
-    // ---- PDL prologue: nothing an earlier kernel wrote may be READ before pdl_wait(), but the rows this
-    // warp starts with can already be pulled into L2 (a prefetch has no architectural effect), so the
-    // DRAM latency of the pipeline fill overlaps the tail of the previous kernel.
-    if (task < g.tasks) {
-        const long long grp0 = task / g.strips;
-        const long long pos0 = (g.total_rows * grp0) / g.groups;
-        const int colp = min(max((int)(task % g.strips) * kStripCols + (lane - 1) * kVec, 0), g.W - 1);
+    // task id -> (strip, first row, end row): equal row ranges (+-1 row), `strips` tasks per range
+    // Tasks are handed out from the END of the shard backwards: the pointwise forward is a front-to-back
+    // stream, so the last ~100 MB of x and t it read are still in the 126 MB L2 when this kernel starts.
+    auto decode = [&](long long tk, int& strip_o, long long& pos_o, long long& end_o) {
+        if (A.reverse) tk = g.tasks - 1 - tk;
+        strip_o = (int)(tk % g.strips);
+        const long long grp = tk / g.strips;
+        pos_o = (g.total_rows * grp) / g.groups;
+        end_o = (g.total_rows * (grp + 1)) / g.groups;
+    };
+    // pull the rows a range starts with (2 halo rows + the pipeline depth) into L2; no architectural effect
+    auto prefetch_rows = [&](int strip_p, long long pos_p) {
         if ((lane & 7) == 0 || lane == 31) {
-            const char* xp = reinterpret_cast<const char*>(A.x) + (pos0 * g.W + colp) * (long long)sizeof(XT);
-            const char* tp = reinterpret_cast<const char*>(A.t) + (pos0 * g.W + colp) * (long long)sizeof(TT);
+            const int colp = min(max(strip_p * kStripCols + (lane - 1) * kVec, 0), g.W - 1);
+            const char* xp = reinterpret_cast<const char*>(A.x) + (pos_p * g.W + colp) * (long long)sizeof(XT);
+            const char* tp = reinterpret_cast<const char*>(A.t) + (pos_p * g.W + colp) * (long long)sizeof(TT);
 #pragma unroll
             for (int q = -2; q < kStages; ++q) {
-                if (pos0 + q >= 0 && pos0 + q < g.total_rows) {
+                if (pos_p + q >= 0 && pos_p + q < g.total_rows) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + (long long)q * g.W * (long long)sizeof(XT)));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + (long long)q * g.W * (long long)sizeof(TT)));
                 }
             }
         }
+    };
+
+    // ---- PDL prologue: nothing an earlier kernel wrote may be READ before pdl_wait(), but the rows this
+    // warp starts with can already be pulled into L2 (a prefetch has no architectural effect), so the
+    // DRAM latency of the pipeline fill overlaps the tail of the previous kernel.
+    if (task < g.tasks) {
+        int strip_p;
+        long long pos_p, end_p;
+        decode(task, strip_p, pos_p, end_p);
+        prefetch_rows(strip_p, pos_p);
     }
     pdl_wait();
     pdl_launch_dependents();
+    TL_STAMP(1, 1);
 
     // ---- global sums: given, or (data parallel) collected from the peer mailbox -----------------
     __shared__ double s_gs[PIL_NSUMS];
@@ -1067,7 +1119,7 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
 
     if (task >= g.tasks) {
         if (A.accumulate) {  // idle warp of the last block still takes part in the block reduction
-            const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const double zero[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             bwd_epilogue(A, zero, gs);
         }
         return;
@@ -1095,15 +1147,27 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         c.D = (float)A.p.diffusion_coeff;
         c.a1 = (float)(1.0 + A.p.reaction_threshold);
         c.c0 = (float)(-A.p.reaction_threshold - 4.0 * A.p.diffusion_coeff);
+        c.beta_half = 0.5f * c.beta;
+        c.f1c = (float)(-A.p.reaction_threshold * crd - 4.0 * crd * A.p.diffusion_coeff);
+        c.cW2n = -2.0f * c.cW;
     }
 
-    const int strip = (int)(task % g.strips);
-    const long long grp = task / g.strips;
-    long long pos = (g.total_rows * grp) / g.groups;              // flattened image row b*H + r
-    const long long end = (g.total_rows * (grp + 1)) / g.groups;
+    // ---- task loop.  Equal static row ranges finish far apart (measured: 83..145 us per block at
+    // 64x1024^2 -- SMs do not get equal shares of the memory system), and with one resident wave nothing
+    // evens that out.  So the ranges are made short and, after its first one, every warp claims the next
+    // unprocessed (range, strip) task from a global counter until none is left.
     const int H = g.H, W = g.W;
-    const int col0 = strip * kStripCols + (lane - 1) * kVec;
     const bool out_lane = (lane >= 1) && (lane <= kOutLanes);
+    double tot_r2 = 0.0, tot_g2 = 0.0;  // stencil sums over all tasks of this thread (task partials are fp32)
+    long long task_cur = task;
+#pragma unroll 1
+  for (;;) {
+    int strip;
+    long long pos, end;  // flattened image rows b*H + r of this task
+    decode(task_cur, strip, pos, end);
+    // claim the NEXT task now and pull its first rows into L2, so that the pipeline fill of the next
+    // range costs an L2 round trip instead of a DRAM one (a range is only a few tens of microseconds)
+    const int col0 = strip * kStripCols + (lane - 1) * kVec;
     const bool in_img = col0 >= 0 && col0 < W;  // ALIGNED: whole vector in the image
 
     Cols<ALIGNED> cx;
@@ -1119,6 +1183,9 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         mc[p] = in ? 1.0f : 0.0f;
         fc[p] = in ? ((cc == 0 || cc == W - 1) ? 2.0f : 1.0f) : 0.0f;
     }
+    // packed path: the same factors folded into per-slot coefficient pairs
+    const f2 cAf2[2] = {make_float2(c.cA * fc[0], c.cA * fc[1]), make_float2(c.cA * fc[2], c.cA * fc[3])};
+    const f2 cGm2[2] = {make_float2(c.cG * mc[0], c.cG * mc[1]), make_float2(c.cG * mc[2], c.cG * mc[3])};
     const bool store_vec = ALIGNED && out_lane && in_img;
     // stencil sums of the rows this warp owns (accumulate mode): sum r^2 and sum dx^2+dy^2
     f2 sr2 = make_float2(0.f, 0.f), sg2 = make_float2(0.f, 0.f);
@@ -1256,9 +1323,18 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         }
     };
 
-    // Packed (fp32x2) form of the same iteration for the ALIGNED path: identical arithmetic, two
-    // pixels per issue slot.  Pairs are (slot0,slot1) and (slot2,slot3); horizontal neighbours come
-    // from the three shifted pairs A=(L,s0) B=(s1,s2) C=(s3,R).
+    // Packed (fp32x2) form of the same iteration for the ALIGNED path.  Pairs are (slot0,slot1) and
+    // (slot2,slot3).  The kernel is bound by FMA-pipe cycles (a packed op holds the pipe for two), so the
+    // arithmetic is arranged to minimise them:
+    //   * everything that combines HORIZONTAL neighbours is done with scalar adds on the six values
+    //     {L, s0..s3, R}: a scalar add costs the pipe what half a packed add does, and it avoids the
+    //     register moves that forming misaligned pairs (L,s0) (s1,s2) (s3,R) would need;
+    //   * the transposed horizontal stencils travel as two combined quantities instead of four:
+    //         Ah = cA*fc*r + cG*mc*dx   goes to the RIGHT neighbour,   Bh = cA*fc*r - cG*mc*dx   to the LEFT
+    //     (fc/mc: image-edge column factors, folded into per-slot constants), 2 shuffles instead of 4;
+    //   * the Dice constant beta rides along: Ah and Bh each carry beta/2 and every pixel receives
+    //     exactly one of each, so the emission needs no separate "+ beta";
+    //   * -4*cA*r joins the reaction derivative: (cF f'(u) - 4 cA) * r, one FMA.
     auto compute_packed = [&](int k, auto check, const float4& xn, const float4& tn, const float4& ua, const float4& ub,
                               float4& uc4, float4& gm4, float4& g04, float4& gp4) {
         constexpr bool CHECK = decltype(check)::value;
@@ -1272,49 +1348,44 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
             const float L = __shfl_up_sync(0xffffffffu, ub.w, 1);
             const float R = __shfl_down_sync(0xffffffffu, ub.x, 1);
             const f2 u[2] = {make_float2(ub.x, ub.y), make_float2(ub.z, ub.w)};
-            const f2 eA = make_float2(L, ub.x), eB = make_float2(ub.y, ub.z), eC = make_float2(ub.w, R);
-            const f2 lf[2] = {eA, eB}, rt[2] = {eB, eC};
-            f2 r[2], dx[2];
+            // horizontal neighbour sums and differences, scalar (src/pde.py:73-77, :172)
+            const f2 hs[2] = {make_float2(L + ub.y, ub.x + ub.z), make_float2(ub.y + ub.w, ub.z + R)};
+            const f2 dx[2] = {make_float2(ub.y - L, ub.z - ub.x), make_float2(ub.w - ub.y, R - ub.z)};
+            f2 r[2], dy[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const f2 s4 = add2(add2(lf[h], rt[h]), add2(va[h], vc[h]));
+                const f2 s4 = add2(hs[h], add2(va[h], vc[h]));
                 // r = D*(s4 - 4u) + u(1-u)(u-a), as a polynomial in u   (src/pde.py:73-77,:99,:120)
                 r[h] = fma2(u[h], fma2(u[h], sub2(bc(c.a1), u[h]), bc(c.c0)), mul2(bc(c.D), s4));
-                dx[h] = sub2(rt[h], lf[h]);
+                dy[h] = sub2(vc[h], va[h]);
             }
             if (!CHECK || (k >= r0 && k < r1)) {  // rows this segment owns: loss terms the light forward skipped
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const f2 dy = sub2(vc[h], va[h]);
                     sr2 = fma2(r[h], r[h], sr2);
                     sg2 = fma2(dx[h], dx[h], sg2);
-                    sg2 = fma2(dy, dy, sg2);
+                    sg2 = fma2(dy[h], dy[h], sg2);
                 }
             }
-            // only slots 0 and 3 can be an image-edge column or feed a neighbour lane
-            const float rc0 = r[0].x * fc[0], rc3 = r[1].y * fc[3];
-            dx[0].x *= mc[0];
-            dx[1].y *= mc[3];
-            const float rL = __shfl_up_sync(0xffffffffu, rc3, 1);
-            const float rR = __shfl_down_sync(0xffffffffu, rc0, 1);
-            const float dL = __shfl_up_sync(0xffffffffu, dx[1].y, 1);
-            const float dR = __shfl_down_sync(0xffffffffu, dx[0].x, 1);
-            const f2 rA = make_float2(rL, rc0), rB = make_float2(r[0].y, r[1].x), rC = make_float2(rc3, rR);
-            const f2 dA = make_float2(dL, dx[0].x), dB = make_float2(dx[0].y, dx[1].x), dC = make_float2(dx[1].y, dR);
-            const f2 rl[2] = {rA, rB}, rr[2] = {rB, rC}, dl[2] = {dA, dB}, dr[2] = {dB, dC};
             // row factor of the transposed vertical stencil; dy of an edge row is 0 by mirroring
             const float cAr = (CHECK && (k == 0 || k == H - 1)) ? 2.0f * c.cA : c.cA;
+            f2 Ah[2], Bh[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const f2 ey = mul2(bc(c.cG), sub2(vc[h], va[h]));
-                gp[h] = fma2(bc(cAr), r[h], ey);                 // into row k+1
-                gm[h] = fma2(bc(cAr), r[h], sub2(gm[h], ey));    // into row k-1
-                const f2 fpr = fma2(u[h], fma2(bc(c.f3), u[h], bc(c.f2)), bc(c.f1));  // cF * f'(u)
-                f2 acc = g0[h];
-                acc = fma2(bc(c.cA), fma2(bc(-4.0f), r[h], add2(rl[h], rr[h])), acc);
-                acc = fma2(fpr, r[h], acc);
-                acc = fma2(bc(c.cG), sub2(dl[h], dr[h]), acc);
-                g0[h] = acc;
+                const f2 qv = mul2(bc(cAr), r[h]);
+                gp[h] = fma2(bc(c.cG), dy[h], qv);                     // into row k+1:  cA r + cG dy
+                gm[h] = add2(gm[h], fma2(bc(-c.cG), dy[h], qv));       // into row k-1:  cA r - cG dy
+                const f2 qf = fma2(cAf2[h], r[h], bc(c.beta_half));
+                Ah[h] = fma2(cGm2[h], dx[h], qf);
+                Bh[h] = fma2(make_float2(-cGm2[h].x, -cGm2[h].y), dx[h], qf);
+            }
+            const float AL = __shfl_up_sync(0xffffffffu, Ah[1].y, 1);    // from the pixel left of slot 0
+            const float BR = __shfl_down_sync(0xffffffffu, Bh[0].x, 1);  // from the pixel right of slot 3
+            const f2 hg[2] = {make_float2(AL + Bh[0].y, Ah[0].x + Bh[1].x), make_float2(Ah[0].y + Bh[1].y, Ah[1].x + BR)};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const f2 fpr = fma2(u[h], fma2(bc(c.f3), u[h], bc(c.f2)), bc(c.f1c));  // cF f'(u) - 4 cA
+                g0[h] = fma2(fpr, r[h], add2(g0[h], hg[h]));
             }
         } else {
             gp[0] = gp[1] = make_float2(0.f, 0.f);
@@ -1323,7 +1394,7 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         gp4 = make_float4(gp[0].x, gp[0].y, gp[1].x, gp[1].y);
 
         if (!CHECK || k - 1 >= r0) {
-            // emit gradient row k-1 : pointwise terms + accumulated stencil terms, then the chain factor
+            // emit gradient row k-1 : pointwise terms + accumulated stencil terms (beta included), chain factor
             const f2 vt[2] = {make_float2(tn.x, tn.y), make_float2(tn.z, tn.w)};
             f2 o[2];
 #pragma unroll
@@ -1331,8 +1402,8 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
                 const f2 u = va[h], t = vt[h];
                 const f2 v = sub2(bc(1.0f), u);
                 const f2 uv = mul2(u, v);
-                f2 du = add2(gm[h], fma2(bc(c.alpha), t, bc(c.beta)));
-                du = fma2(mul2(bc(c.cW), uv), sub2(v, u), du);
+                // du = gm + alpha t + cW uv (1-2u)
+                const f2 du = fma2(uv, fma2(bc(c.cW2n), u, bc(c.cW)), fma2(bc(c.alpha), t, gm[h]));
                 const f2 w = mul2(bc(c.cb), sub2(u, t));
                 if constexpr (KIND == PIL_X_PROB) {
                     const f2 inv = make_float2(rcp_approx(fmaxf(uv.x, 1e-12f)), rcp_approx(fmaxf(uv.y, 1e-12f)));
@@ -1449,18 +1520,32 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
     }
   }  // segments
 
-    if (!A.accumulate) return;  // uniform: plain pil_backward
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if constexpr (ALIGNED) {
         if (store_vec) {
-            acc[4] = sr2.x + sr2.y;
-            acc[5] = sg2.x + sg2.y;
+            tot_r2 += (double)(sr2.x + sr2.y);
+            tot_g2 += (double)(sg2.x + sg2.y);
         }
     } else {
-        acc[4] = sr2s;
-        acc[5] = sg2s;
+        tot_r2 += (double)sr2s;
+        tot_g2 += (double)sg2s;
     }
+    // claim the next unprocessed task.  (Claiming earlier -- to prefetch the next range -- was measured
+    // to lose more than it gains: a task held in reserve is not available to a warp that runs dry.)
+    if (A.task_counter == nullptr) break;
+    unsigned int claimed = 0u;
+    if (lane == 0) claimed = atomicAdd(A.task_counter, 1u);
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    task_cur = A.first_dynamic + (long long)claimed;
+    if (task_cur >= g.tasks) break;
+  }  // tasks
+
+    TL_STAMP(1, 2);
+    if (!A.accumulate) return;  // uniform: plain pil_backward
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    acc[4] = tot_r2;
+    acc[5] = tot_g2;
     bwd_epilogue(A, acc, gs);
+    TL_STAMP(1, 3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1673,6 +1758,25 @@ static cudaError_t launch_pdl(K kernel, int blocks, int threads, int smem, cudaS
     return cudaLaunchKernelEx(&cfg, kernel, args);
 }
 
+// Rows per dynamically claimed range of the backward kernel.  PIL_BWD_ROWS forces a value (0 = static
+// partition).  Automatic: 64 rows -- long enough to amortise the 4 halo rows and the pipeline fill of a
+// range, short enough to balance.  Measured on B200 at 64x1024^2 fp32: static 157.8 us; dynamic 24 rows
+// 169.9, 32: 157.5, 48: 155.6, 61: 149-153, 63: 150.5, 64: 145-147, 67: 152, 96: 149.5, 128: 155.7 (the
+// power of two wins over its neighbours: range boundaries then tile the 2 MB pages).  Shrinking ranges
+// (guided self-scheduling), a small-range tail phase and claiming one range ahead to prefetch it were all
+// measured slower.  Problems too small for ~2.5 waves of such ranges keep the static one-wave partition.
+static int bwd_dynamic_rows(long long total_rows, long long strips, long long resident_warps) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("PIL_BWD_ROWS");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0) return (forced > 0 && forced < kMinRows) ? kMinRows : forced;
+    const int rows = 64;
+    const double waves = (double)(((total_rows + rows - 1) / rows) * strips) / (double)resident_warps;
+    return waves < 2.5 ? 0 : rows;
+}
+
 static unsigned long long xchg_timeout_ns() {
     static unsigned long long v = 0;
     if (v == 0) {
@@ -1756,8 +1860,23 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
             cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             per_sm = blocks_per_sm(kernel, smem);
         }
-        a.g = make_geo(B, H, W, sm_count() * per_sm, g_tune_bwd_rps, tuning_waves(true, B, H, W, sm_count() * per_sm));
-        out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        const int resident = sm_count() * per_sm;
+        const long long strips_ = (W + kStripCols - 1) / kStripCols;
+        const int dyn_rows = a.task_counter != nullptr
+                                 ? (g_tune_bwd_rps > 0 ? g_tune_bwd_rps : bwd_dynamic_rows(B * H, strips_, (long long)resident * kWarpsPerBlock))
+                                 : 0;
+        if (dyn_rows > 0) {
+            // persistent grid of the resident blocks; short ranges claimed dynamically (see the kernel)
+            a.g = make_geo(B, H, W, resident, dyn_rows, 1);
+            const long long need = (a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+            out->blocks = (int)(need < resident ? need : resident);
+            a.first_dynamic = (long long)out->blocks * kWarpsPerBlock;
+        } else {
+            a.task_counter = nullptr;
+            a.first_dynamic = 0;
+            a.g = make_geo(B, H, W, resident, g_tune_bwd_rps, tuning_waves(true, B, H, W, resident));
+            out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        }
         out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
         return launch_pdl(kernel, out->blocks, kThreads, smem, s, a);
     };
@@ -1995,6 +2114,8 @@ static int backward_impl(const void* x, const void* t, void* grad, int64_t B, in
     }
     a.partials = nullptr;
     a.ticket = nullptr;
+    a.task_counter = nullptr;
+    a.first_dynamic = 0;
     a.stencil_sums = stencil_sums;
     a.loss_out = loss_out;
     a.total_sums = total_sums;
@@ -2003,6 +2124,7 @@ static int backward_impl(const void* x, const void* t, void* grad, int64_t B, in
     if (a.accumulate) {
         const WorkspaceLayout wl = workspace_layout(B, H, W);
         a.ticket = reinterpret_cast<unsigned int*>((char*)acc_ws + wl.ticket_off);
+        a.task_counter = a.ticket + 1;
         a.partials = reinterpret_cast<double*>((char*)acc_ws + wl.partials_off);
     }
     const bool aligned = is_aligned_case(x, t, grad, W, x_dtype, t_dtype);
@@ -2235,6 +2357,10 @@ int pil_last_launch_info(PilLaunchInfo* out) {
     out->kernels_launched = g_kernels_launched;
     return PIL_OK;
 }
+
+#ifdef PIL_TIMELINE
+int pil_debug_timeline(void* buf) { return (int)cudaMemcpyToSymbol(pil::g_timeline, &buf, sizeof(buf)); }
+#endif
 
 int pil_set_tuning(int fwd_rows_per_segment, int bwd_rows_per_segment) {
     g_tune_fwd_rps = fwd_rows_per_segment > 0 ? fwd_rows_per_segment : 0;
