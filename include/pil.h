@@ -35,6 +35,8 @@ extern "C" {
 #define PIL_NSUMS 8
 /* Number of floats in a loss-report vector (see pil_finalize). */
 #define PIL_NOUT 8
+/* Number of doubles in a moments vector (see pil_forward_moments). */
+#define PIL_NMOMENTS 16
 
 typedef enum PilStatus {
     PIL_OK = 0,
@@ -170,6 +172,26 @@ int pil_loss_fwd_bwd(const void* x, const void* t, void* grad, int64_t B, int64_
 int pil_scale_gradient(void* grad, int dtype, int64_t n, const float* upstream, void* stream);
 
 /*
+ * Parameter sweeps (BASELINE config 4; the S2/S3 sensitivity grids of run_ablation.py:159-224 evaluated as
+ * ONE batched loss evaluation).  lap(u), g = u(1-u), h = g*u, |grad u|^2 and the Dice/BCE sums do not
+ * depend on D, a, eps or the weights, and r = D*lap + h - a*g, so the loss for ANY setting of the knobs is a
+ * closed form in 13 parameter-independent sums.  pil_forward_moments makes one pass over the maps (same
+ * fused kernel as pil_forward, 8 B/px) and pil_sweep_finalize turns the moments into n_params loss
+ * reports (a one-block kernel; no further pass over the maps).
+ *
+ * moments (device, PIL_NMOMENTS doubles) for THIS shard -- all-reduce (SUM) across ranks before finalising:
+ *   [0] I  [1] P  [2] T  [3] sum BCE terms  [4] sum lap^2  [5] sum gx^2+gy^2  [6] sum g^2  [7] n_invalid
+ *   [8] sum lap*h  [9] sum lap*g  [10] sum h^2  [11] sum h*g  [12] n_pixels  [13..15] 0
+ * params: HOST array of n_params settings (validated like pil_validate_params); loss_out: device,
+ * n_params x PIL_NOUT floats, row k laid out like pil_finalize's loss_out for params[k].
+ */
+int pil_forward_moments(const void* x, const void* t, int64_t B, int64_t H, int64_t W,
+                        int x_dtype, int t_dtype, int x_kind,
+                        double* moments, void* workspace, size_t workspace_bytes, void* stream);
+int pil_sweep_finalize(const double* moments, int64_t n_global, const PilParams* params, int n_params,
+                       float* loss_out, void* stream);
+
+/*
  * Data-parallel training step over PEER MEMORY (one process per GPU of one NVLink/NVSwitch node).
  * The batch shards by whole images (every image has its own mirror boundary, src/pde.py:67, so no halo
  * exchange); the only coupling is the batch-global reductions of src/loss.py:134-141 and
@@ -248,6 +270,13 @@ int pil_session_create(PilSession** out, int device, int64_t max_B, int64_t H, i
                        int x_dtype, int t_dtype);
 int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B,
                     int x_kind, const PilParams* p, float* loss_out_host);
+/* flags for pil_session_run_ex.  PIL_SESSION_GRAD_ON_DEVICE (with grad_host == NULL): forward AND backward
+ * run, the gradient stays in the session's device buffer (pil_session_grad_ptr; valid until the next
+ * run) the way a training step consumes it, and only the loss report crosses back to the host. */
+#define PIL_SESSION_GRAD_ON_DEVICE 1
+int pil_session_run_ex(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B,
+                       int x_kind, const PilParams* p, float* loss_out_host, int flags);
+void* pil_session_grad_ptr(PilSession* s);
 int pil_session_destroy(PilSession* s);
 
 /* Introspection for tests/benchmarks: how the last launch on this thread was tiled. */

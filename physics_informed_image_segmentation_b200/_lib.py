@@ -24,6 +24,7 @@ NVCC_FLAGS = [
 
 PIL_NSUMS = 8
 PIL_NOUT = 8
+PIL_NMOMENTS = 16
 F32, BF16, U8 = 0, 1, 2
 X_PROB, X_LOGITS_SIGMOID, X_LOGITS_TANH = 0, 1, 2
 
@@ -43,6 +44,7 @@ class PilLaunchInfo(ctypes.Structure):
 PIL_MAX_RANKS = 8
 PIL_IPC_HANDLE_BYTES = 64
 PIL_XCHG_DEFER_FINALIZE = 1
+PIL_SESSION_GRAD_ON_DEVICE = 1
 
 
 class PilExchange(ctypes.Structure):
@@ -97,6 +99,11 @@ _SIGS = {
     "pil_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PilParams),
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "pil_forward_moments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_size_t, ctypes.c_void_p]),
+    "pil_sweep_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(PilParams), ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
     "pil_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(PilParams), ctypes.c_void_p,
                                     ctypes.c_void_p]),
     "pil_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
@@ -143,6 +150,9 @@ _SIGS = {
                                           ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "pil_session_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_int64, ctypes.c_int, ctypes.POINTER(PilParams), ctypes.c_void_p]),
+    "pil_session_run_ex": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int64, ctypes.c_int, ctypes.POINTER(PilParams), ctypes.c_void_p, ctypes.c_int]),
+    "pil_session_grad_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "pil_session_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pil_last_launch_info": (ctypes.c_int, [ctypes.POINTER(PilLaunchInfo)]),
     "pil_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),

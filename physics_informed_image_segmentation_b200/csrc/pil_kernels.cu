@@ -495,27 +495,29 @@ __device__ __noinline__ void xchg_wait_sum(const XchgDev& X, int phase, double* 
 // *ticket to 0 when it is done (so the workspace is reusable by the next launch on the stream).
 // accumulator layout: 0 I, 1 P, 2 T, 3 bce (log2 units, un-negated), 4 r^2, 5 dx^2+dy^2, 6 (uv)^2, 7 #invalid
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, typename AccT>
+template <int THREADS, typename AccT, int N = PIL_NSUMS>
 __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* partials, unsigned int* ticket, double* out) {
     constexpr int kWarps = THREADS / 32;
-    __shared__ double s_part[kWarps][PIL_NSUMS];
+    constexpr int NP = N / 2;  // component pairs (16-byte loads)
+    static_assert(N % 2 == 0 && THREADS % NP == 0, "component layout");
+    __shared__ double s_part[kWarps][N];
     __shared__ double s_red[2 * THREADS];
-    __shared__ double s_tot[PIL_NSUMS];
+    __shared__ double s_tot[N];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < N; ++k) {
         AccT v = acc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) s_part[warp][k] = (double)v;
     }
     __syncthreads();
-    if (threadIdx.x < PIL_NSUMS) {
+    if (threadIdx.x < N) {
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) v += s_part[w][threadIdx.x];
-        partials[(long long)blockIdx.x * PIL_NSUMS + threadIdx.x] = v;
+        partials[(long long)blockIdx.x * N + threadIdx.x] = v;
         __threadfence();
     }
     __syncthreads();
@@ -526,12 +528,13 @@ __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* pa
     __syncthreads();
     if (!s_last) return false;
     __threadfence();
+    constexpr int kGroups = THREADS / NP;
     {
-        // THREADS/4 block-groups x 4 component PAIRS: 16-byte L2 loads, 8 in flight per thread (the tail
+        // kGroups block-groups x NP component PAIRS: 16-byte L2 loads, 8 in flight per thread (the tail
         // batch is predicated, not serialised), fixed order -> bit-reproducible.  This is serial time
         // at the very end of the kernel, so it is kept to 2-3 L2 round trips.
-        constexpr int kGroups = THREADS / 4, kIlp = 8;
-        const int c2 = threadIdx.x & 3, j = threadIdx.x >> 2;
+        constexpr int kIlp = 8;
+        const int c2 = threadIdx.x % NP, j = threadIdx.x / NP;
         const long long nb = gridDim.x;
         double vx = 0.0, vy = 0.0;
         for (long long blk = j; blk < nb; blk += (long long)kIlp * kGroups) {
@@ -539,7 +542,7 @@ __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* pa
 #pragma unroll
             for (int q = 0; q < kIlp; ++q) {
                 const long long b = blk + (long long)q * kGroups;
-                w[q] = (b < nb) ? __ldcg(reinterpret_cast<const double2*>(partials + b * PIL_NSUMS) + c2) : make_double2(0.0, 0.0);
+                w[q] = (b < nb) ? __ldcg(reinterpret_cast<const double2*>(partials + b * N) + c2) : make_double2(0.0, 0.0);
             }
 #pragma unroll
             for (int q = 0; q < kIlp; ++q) {
@@ -547,19 +550,19 @@ __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* pa
                 vy += w[q].y;
             }
         }
-        s_red[2 * threadIdx.x] = vx;       // s_red viewed as [kGroups][8]
+        s_red[2 * threadIdx.x] = vx;       // s_red viewed as [kGroups][N]
         s_red[2 * threadIdx.x + 1] = vy;
     }
     __syncthreads();
-    if (threadIdx.x < PIL_NSUMS) {
+    if (threadIdx.x < N) {
         double v = 0.0;
-        for (int j = 0; j < THREADS / 4; ++j) v += s_red[j * 8 + threadIdx.x];
+        for (int j = 0; j < kGroups; ++j) v += s_red[j * N + threadIdx.x];
         s_tot[threadIdx.x] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < PIL_NSUMS; ++k) out[k] = s_tot[k];
+        for (int k = 0; k < N; ++k) out[k] = s_tot[k];
     }
     return true;
 }
@@ -579,11 +582,16 @@ __device__ __forceinline__ void sums_from_raw(const double* raw, double eps, dou
 // ------------------------------------------------------------------------------------------------
 // K1: fused forward
 // ------------------------------------------------------------------------------------------------
-template <int KIND, bool ALIGNED>
+// MOMENTS (pil_forward_moments, the parameter-sweep entry): instead of sum r^2 for ONE (D, a) the row
+// accumulates the parameter-independent second moments of {lap, g = u(1-u), h = g*u}; r = D*lap + h - a*g,
+// so sum r^2 for ANY (D, a) is a quadratic form in them (include/pil.h).
+template <int KIND, bool ALIGNED, bool MOMENTS = false>
 struct FwdRow {
-    // accumulators: 0 I, 1 P, 2 T, 3 sum(t*max(lg2 u,c) + (1-t)*max(lg2(1-u),c)), 4 sum r^2,
+    // accumulators: 0 I, 1 P, 2 T, 3 sum(t*max(lg2 u,c) + (1-t)*max(lg2(1-u),c)), 4 sum r^2 (MOMENTS: sum lap^2),
     //               5 sum dx^2+dy^2 (raw differences), 6 sum (u(1-u))^2, 7 #invalid
-    float acc[8];
+    //     MOMENTS:  8 sum lap*h, 9 sum lap*g, 10 sum h^2, 11 sum h*g, 12..15 unused
+    float acc[MOMENTS ? 16 : 8];
+    f2 ma[4];  // MOMENTS, packed path: 8..11
     float D, a;
     float m[4];  // !ALIGNED: 1 for slots that are real output pixels of this thread
 
@@ -592,10 +600,16 @@ struct FwdRow {
     __device__ __forceinline__ void init_packed() {
 #pragma unroll
         for (int k = 0; k < 7; ++k) pa[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ma[k] = make_float2(0.f, 0.f);
     }
     __device__ __forceinline__ void fold_packed() {
 #pragma unroll
         for (int k = 0; k < 7; ++k) acc[k] = pa[k].x + pa[k].y;
+        if constexpr (MOMENTS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[8 + k] = ma[k].x + ma[k].y;
+        }
     }
     // ---- packed forward, split in two so that the BCE logarithms can reuse the sigmoid's internals ----
     // point2(): activation + every per-pixel term of a pixel pair (I, P, T, BCE, double well).
@@ -651,9 +665,19 @@ struct FwdRow {
     float a1, c0;  // 1+a, -a-4D
     __device__ __forceinline__ void stencil2(f2 u, f2 lf, f2 rt, f2 m, f2 p) {
         const f2 s4 = add2(add2(lf, rt), add2(m, p));                                       // src/pde.py:73-77
-        const f2 r = fma2(u, fma2(u, sub2(bc(a1), u), bc(c0)), mul2(bc(D), s4));            // src/pde.py:99,:120
         const f2 dx = sub2(rt, lf), dy = sub2(p, m);                                        // 2*gx, 2*gy (src/pde.py:172-173)
-        pa[4] = fma2(r, r, pa[4]);
+        if constexpr (MOMENTS) {
+            const f2 lap = fma2(bc(-4.0f), u, s4);
+            const f2 gq = mul2(u, sub2(bc(1.0f), u)), hq = mul2(gq, u);
+            pa[4] = fma2(lap, lap, pa[4]);
+            ma[0] = fma2(lap, hq, ma[0]);
+            ma[1] = fma2(lap, gq, ma[1]);
+            ma[2] = fma2(hq, hq, ma[2]);
+            ma[3] = fma2(hq, gq, ma[3]);
+        } else {
+            const f2 r = fma2(u, fma2(u, sub2(bc(a1), u), bc(c0)), mul2(bc(D), s4));        // src/pde.py:99,:120
+            pa[4] = fma2(r, r, pa[4]);
+        }
         pa[5] = fma2(dx, dx, pa[5]);
         pa[5] = fma2(dy, dy, pa[5]);
     }
@@ -683,12 +707,21 @@ struct FwdRow {
             const float lu = fmaxf(lg2_approx(u), kLogClampLog2);
             const float lv = fmaxf(lg2_approx(v), kLogClampLog2);
             const float b = fmaf(t, lu - lv, lv);  // t*lu + (1-t)*lv
+            if constexpr (MOMENTS) {
+                const float w = ALIGNED ? 1.0f : m[p];
+                const float hq = uv * u;
+                acc[8] = fmaf(lap * hq, w, acc[8]);
+                acc[9] = fmaf(lap * uv, w, acc[9]);
+                acc[10] = fmaf(hq * hq, w, acc[10]);
+                acc[11] = fmaf(hq * uv, w, acc[11]);
+            }
+            const float r4 = MOMENTS ? lap : r;  // slot 4 holds sum lap^2 in MOMENTS mode
             if constexpr (ALIGNED) {
                 acc[0] = fmaf(u, t, acc[0]);
                 acc[1] += u;
                 acc[2] += t;
                 acc[3] += b;
-                acc[4] = fmaf(r, r, acc[4]);
+                acc[4] = fmaf(r4, r4, acc[4]);
                 acc[5] = fmaf(dx, dx, acc[5]);
                 acc[5] = fmaf(dy, dy, acc[5]);
                 acc[6] = fmaf(uv, uv, acc[6]);
@@ -699,7 +732,7 @@ struct FwdRow {
                 acc[1] = fmaf(u, w, acc[1]);
                 acc[2] = fmaf(t, w, acc[2]);
                 acc[3] = fmaf(b, w, acc[3]);
-                acc[4] = fmaf(r * r, w, acc[4]);
+                acc[4] = fmaf(r4 * r4, w, acc[4]);
                 acc[5] = fmaf(dx * dx + dy * dy, w, acc[5]);
                 acc[6] = fmaf(uv * uv, w, acc[6]);
                 if constexpr (KIND == PIL_X_PROB) acc[7] += (u >= 0.0f && u <= 1.0f) ? 0.0f : w;
@@ -708,15 +741,16 @@ struct FwdRow {
     }
 };
 
-template <int KIND, typename XT, typename TT, bool ALIGNED>
-__global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const FwdArgs A) {
+template <int KIND, typename XT, typename TT, bool ALIGNED, bool MOMENTS>
+__global__ void __launch_bounds__(kThreads, MOMENTS ? kFwdMinBlocks - 1 : kFwdMinBlocks) pil_fwd_kernel(const FwdArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Geo& g = A.g;
     const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
 
-    FwdRow<KIND, ALIGNED> fr;
+    constexpr int NACC = MOMENTS ? 16 : 8;
+    FwdRow<KIND, ALIGNED, MOMENTS> fr;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) fr.acc[k] = 0.f;
+    for (int k = 0; k < NACC; ++k) fr.acc[k] = 0.f;
     fr.init_packed();
     fr.D = A.D;
     fr.a = A.a;
@@ -873,12 +907,35 @@ __global__ void __launch_bounds__(kThreads, kFwdMinBlocks) pil_fwd_kernel(const 
             fr.fold_packed();
             if (!counted) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) fr.acc[k] = 0.f;
+                for (int k = 0; k < NACC; ++k) fr.acc[k] = 0.f;
             }
         }
     }
 
     // ---- deterministic cross-block reduction; the last block finalises --------------------------
+    if constexpr (MOMENTS) {
+        double raw[16];
+        if (!reduce_to_last_block<kThreads, float, 16>(fr.acc, A.partials, A.ticket, raw)) return;
+        if (threadIdx.x == 0) {  // layout: include/pil.h PIL_NMOMENTS
+            double* mo = A.sums;
+            mo[0] = raw[0];
+            mo[1] = raw[1];
+            mo[2] = raw[2];
+            mo[3] = -(double)kLn2 * raw[3];
+            mo[4] = raw[4];            // sum lap^2
+            mo[5] = 0.25 * raw[5];     // sum gx^2 + gy^2
+            mo[6] = raw[6];            // sum g^2 = sum u^2 (1-u)^2
+            mo[7] = raw[7];            // n_invalid
+            mo[8] = raw[8];            // sum lap*h
+            mo[9] = raw[9];            // sum lap*g
+            mo[10] = raw[10];          // sum h^2
+            mo[11] = raw[11];          // sum h*g
+            mo[12] = (double)g.B * (double)g.H * (double)g.W;
+            mo[13] = mo[14] = mo[15] = 0.0;
+            *A.ticket = 0u;
+        }
+        return;
+    }
     double raw[PIL_NSUMS];
     if (!reduce_to_last_block<kThreads, float>(fr.acc, A.partials, A.ticket, raw)) return;
     if (threadIdx.x == 0) {
@@ -1563,6 +1620,31 @@ __global__ void pil_finalize_kernel(const double* sums, long long n_global, PilP
     }
 }
 
+// Losses of up to kSweepChunk parameter settings from one moments vector (pil_forward_moments):
+//   sum r^2 = D^2 <lap,lap> + 2D <lap,h> - 2aD <lap,g> + <h,h> - 2a <h,g> + a^2 <g,g>      (r = D lap + h - a g)
+//   sum pf  = (eps/2) sum |grad u|^2 + <g,g> / eps
+constexpr int kSweepChunk = 32;
+struct SweepParams {
+    int n;
+    PilParams p[kSweepChunk];
+};
+__global__ void pil_sweep_finalize_kernel(const double* mo, long long n_global, SweepParams sp, float* out) {
+    const int k = threadIdx.x;
+    if (blockIdx.x != 0 || k >= sp.n) return;
+    const PilParams& p = sp.p[k];
+    const double D = p.diffusion_coeff, a = p.reaction_threshold, eps = p.epsilon;
+    double s[PIL_NSUMS];
+    s[0] = mo[0];
+    s[1] = mo[1];
+    s[2] = mo[2];
+    s[3] = mo[3];
+    s[4] = D * D * mo[4] + 2.0 * D * mo[8] - 2.0 * a * D * mo[9] + mo[10] - 2.0 * a * mo[11] + a * a * mo[6];
+    s[5] = (p.phase_field_weight > 0.0) ? 0.5 * eps * mo[5] + mo[6] / eps : 0.0;
+    s[6] = mo[7];
+    s[7] = mo[12];
+    finalize_device(s, n_global > 0 ? (double)n_global : s[7], p, out + (size_t)k * PIL_NOUT);
+}
+
 // deferred finalisation of a data-parallel step: both exchanged vectors -> the global loss report
 __global__ void __launch_bounds__(kThreads) pil_xchg_finalize_kernel(XchgDev X, long long n_global, PilParams p, float* out, double* total_sums) {
     __shared__ double s_a[PIL_NSUMS], s_b[PIL_NSUMS];
@@ -1805,10 +1887,10 @@ static int make_xchg(const PilExchange* ex, XchgDev* X) {
 
 template <int KIND, typename XT, typename TT>
 static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned, size_t partial_bytes_avail,
-                                cudaStream_t s, LaunchOut* out) {
-    static int per_sm_cache[2] = {0, 0};  // per template instantiation x {scalar, aligned} kernel
+                                cudaStream_t s, LaunchOut* out, bool moments) {
+    static int per_sm_cache[4] = {0, 0, 0, 0};  // per template instantiation x {scalar, aligned} x {sums, moments}
     auto go = [&](auto kernel, int smem) -> cudaError_t {
-        int& per_sm = per_sm_cache[aligned ? 1 : 0];
+        int& per_sm = per_sm_cache[(aligned ? 1 : 0) + (moments ? 2 : 0)];
         if (per_sm == 0) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             per_sm = blocks_per_sm(kernel, smem);
@@ -1816,18 +1898,22 @@ static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, boo
         a.g = make_geo(B, H, W, sm_count() * per_sm, g_tune_fwd_rps, tuning_waves(false, B, H, W, sm_count() * per_sm));
         out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
         out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
-        if ((size_t)out->blocks * PIL_NSUMS * sizeof(double) > partial_bytes_avail) {
+        if ((size_t)out->blocks * (moments ? 16 : PIL_NSUMS) * sizeof(double) > partial_bytes_avail) {
             out->status = PIL_ERR_WORKSPACE;
             return cudaSuccess;
         }
         kernel<<<out->blocks, kThreads, smem, s>>>(a);
         return cudaGetLastError();
     };
-    if (aligned) return go(pil_fwd_kernel<KIND, XT, TT, true>, kSmemPerBlock);
-    return go(pil_fwd_kernel<KIND, XT, TT, false>, 0);
+    if (moments) {
+        if (aligned) return go(pil_fwd_kernel<KIND, XT, TT, true, true>, kSmemPerBlock);
+        return go(pil_fwd_kernel<KIND, XT, TT, false, true>, 0);
+    }
+    if (aligned) return go(pil_fwd_kernel<KIND, XT, TT, true, false>, kSmemPerBlock);
+    return go(pil_fwd_kernel<KIND, XT, TT, false, false>, 0);
 }
-#define PIL_FWD_ARGS FwdArgs &a, int64_t B, int64_t H, int64_t W, bool aligned, size_t avail, cudaStream_t s, LaunchOut *out
-#define PIL_FWD_PASS a, B, H, W, aligned, avail, s, out
+#define PIL_FWD_ARGS FwdArgs &a, int64_t B, int64_t H, int64_t W, bool aligned, size_t avail, cudaStream_t s, LaunchOut *out, bool moments
+#define PIL_FWD_PASS a, B, H, W, aligned, avail, s, out, moments
 template <int KIND, typename XT>
 static cudaError_t launch_fwd_t(int t_dtype, PIL_FWD_ARGS) {
 #ifdef PIL_DEV_F32_ONLY  // development builds: fp32 maps only (6x faster to compile)
@@ -1988,7 +2074,7 @@ static WorkspaceLayout workspace_layout(int64_t B, int64_t H, int64_t W) {
     l.ticket_off = 0;
     l.scratch_off = 64;   // PIL_NSUMS doubles of scratch (pil_loss_fwd_bwd)
     l.partials_off = 256;
-    l.total = l.partials_off + (size_t)(blocks > kMaxPointBlocks ? blocks : kMaxPointBlocks) * PIL_NSUMS * sizeof(double);
+    l.total = l.partials_off + (size_t)(blocks > kMaxPointBlocks ? blocks : kMaxPointBlocks) * PIL_NMOMENTS * sizeof(double);
     return l;
 }
 
@@ -2039,9 +2125,9 @@ int pil_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
     return (int)cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream);
 }
 
-int pil_forward(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,
-                const PilParams* p, double* sums, float* loss_out, void* workspace, size_t workspace_bytes,
-                void* stream) {
+static int forward_impl(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,
+                        const PilParams* p, double* sums, float* loss_out, void* workspace, size_t workspace_bytes,
+                        void* stream, bool moments) {
     int st = check_common(x, t, B, H, W, x_dtype, t_dtype, x_kind, p);
     if (st != PIL_OK) return st;
     if (!sums || !workspace) return PIL_ERR_NULL;
@@ -2064,9 +2150,9 @@ int pil_forward(const void* x, const void* t, int64_t B, int64_t H, int64_t W, i
     LaunchOut lo;
     cudaError_t e;
     switch (x_kind) {
-        case PIL_X_PROB: e = launch_fwd_x<PIL_X_PROB>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo); break;
-        case PIL_X_LOGITS_SIGMOID: e = launch_fwd_x<PIL_X_LOGITS_SIGMOID>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo); break;
-        default: e = launch_fwd_x<PIL_X_LOGITS_TANH>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo); break;
+        case PIL_X_PROB: e = launch_fwd_x<PIL_X_PROB>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo, moments); break;
+        case PIL_X_LOGITS_SIGMOID: e = launch_fwd_x<PIL_X_LOGITS_SIGMOID>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo, moments); break;
+        default: e = launch_fwd_x<PIL_X_LOGITS_TANH>(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo, moments); break;
     }
     if (lo.status != PIL_OK) return lo.status;
     const int blocks = lo.blocks;
@@ -2076,6 +2162,39 @@ int pil_forward(const void* x, const void* t, int64_t B, int64_t H, int64_t W, i
     t_info.fwd_aligned = aligned ? 1 : 0;
     ++g_kernels_launched;
     return (int)e;
+}
+
+int pil_forward(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,
+                const PilParams* p, double* sums, float* loss_out, void* workspace, size_t workspace_bytes,
+                void* stream) {
+    return forward_impl(x, t, B, H, W, x_dtype, t_dtype, x_kind, p, sums, loss_out, workspace, workspace_bytes, stream, false);
+}
+
+// ---- parameter sweeps: one pass over the maps serves any number of (D, a, eps, weights) settings ----
+int pil_forward_moments(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,
+                        double* moments, void* workspace, size_t workspace_bytes, void* stream) {
+    PilParams neutral = {0.5, 0.5, 0.0, 0.0, 1.0, 0.5, 1.0, 1e-6};  // the moments do not depend on any knob
+    return forward_impl(x, t, B, H, W, x_dtype, t_dtype, x_kind, &neutral, moments, nullptr, workspace, workspace_bytes, stream, true);
+}
+
+int pil_sweep_finalize(const double* moments, int64_t n_global, const PilParams* params, int n_params, float* loss_out,
+                       void* stream) {
+    if (!moments || !params || !loss_out) return PIL_ERR_NULL;
+    if (n_params < 1) return PIL_ERR_SHAPE;
+    for (int k = 0; k < n_params; ++k) {
+        const int st = pil_validate_params(params + k);
+        if (st != PIL_OK) return st;
+    }
+    for (int k0 = 0; k0 < n_params; k0 += kSweepChunk) {
+        SweepParams sp;
+        sp.n = n_params - k0 < kSweepChunk ? n_params - k0 : kSweepChunk;
+        for (int k = 0; k < sp.n; ++k) sp.p[k] = params[k0 + k];
+        pil_sweep_finalize_kernel<<<1, kSweepChunk, 0, (cudaStream_t)stream>>>(moments, (long long)n_global, sp, loss_out + (size_t)k0 * PIL_NOUT);
+        ++g_kernels_launched;
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return PIL_OK;
 }
 
 int pil_finalize(const double* sums, int64_t n_global, const PilParams* p, float* loss_out, void* stream) {

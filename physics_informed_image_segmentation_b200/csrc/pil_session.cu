@@ -126,8 +126,13 @@ int pil_session_create(PilSession** out, int device, int64_t max_B, int64_t H, i
     return PIL_OK;
 }
 
-int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B, int x_kind,
-                    const PilParams* p, float* loss_out_host) {
+// flags: PIL_SESSION_GRAD_ON_DEVICE -- run the backward too and leave the gradient in the session's device
+// buffer (pil_session_grad_ptr), the way a training step consumes it; nothing but the loss report is
+// copied back.  This path uses the training split of pil_kernels.cu: the pointwise forward of chunk c
+// overlaps the H2D of chunk c+1, then ONE backward over the whole batch accumulates the stencil sums and
+// finalises the loss.
+static int session_run_impl(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B, int x_kind,
+                            const PilParams* p, float* loss_out_host, int flags) {
     if (!s || !x_host || !t_host || !p || !loss_out_host) return PIL_ERR_NULL;
     if (B < 1 || B > s->max_B) return PIL_ERR_SESSION;
     int st = pil_validate_params(p);
@@ -139,6 +144,7 @@ int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void*
     const int chunks = (int)(B < kMaxChunks ? B : kMaxChunks);
     const int64_t n_global = B * img;
     auto first = [&](int c) { return (B * c) / chunks; };
+    const bool device_grad = (flags & PIL_SESSION_GRAD_ON_DEVICE) != 0 && grad_host == nullptr;
 
     // phase 1: H2D + forward per chunk
     for (int c = 0; c < chunks; ++c) {
@@ -150,13 +156,29 @@ int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void*
                                 cudaMemcpyHostToDevice, s->s_h2d));
         PIL_TRY(cudaEventRecord(s->ev_in[c], s->s_h2d));
         PIL_TRY(cudaStreamWaitEvent(s->s_comp, s->ev_in[c], 0));
-        st = pil_forward((char*)s->dx + off * xs, (char*)s->dt + off * ts, nb, s->H, s->W, s->x_dtype, s->t_dtype, x_kind,
-                         p, s->dsums + (size_t)c * PIL_NSUMS, nullptr, s->ws[c], s->ws_bytes, s->s_comp);
+        if (device_grad) {
+            st = pil_forward_pointwise((char*)s->dx + off * xs, (char*)s->dt + off * ts, nb, s->H, s->W, s->x_dtype, s->t_dtype,
+                                       x_kind, p, s->dsums + (size_t)c * PIL_NSUMS, s->ws[c], s->ws_bytes, s->s_comp);
+        } else {
+            st = pil_forward((char*)s->dx + off * xs, (char*)s->dt + off * ts, nb, s->H, s->W, s->x_dtype, s->t_dtype, x_kind,
+                             p, s->dsums + (size_t)c * PIL_NSUMS, nullptr, s->ws[c], s->ws_bytes, s->s_comp);
+        }
         if (st != PIL_OK) return st;
     }
     double* gs = s->dsums + (size_t)kMaxChunks * PIL_NSUMS;
     pil_add_chunk_sums<<<1, 32, 0, s->s_comp>>>(s->dsums, chunks, gs);
     PIL_TRY(cudaGetLastError());
+    if (device_grad) {
+        // one backward over the whole batch: gradient stays on the device, stencil sums + loss in the same kernel
+        st = pil_backward_accumulate(s->dx, s->dt, s->dg, B, s->H, s->W, s->x_dtype, s->t_dtype, x_kind, p, gs, n_global,
+                                     nullptr, 1.0f, s->dsums /* scratch: chunk rows are consumed */, s->dout, s->ws[0],
+                                     s->ws_bytes, s->s_comp);
+        if (st != PIL_OK) return st;
+        PIL_TRY(cudaMemcpyAsync(s->hout, s->dout, sizeof(float) * PIL_NOUT, cudaMemcpyDeviceToHost, s->s_comp));
+        PIL_TRY(cudaStreamSynchronize(s->s_comp));
+        for (int k = 0; k < PIL_NOUT; ++k) loss_out_host[k] = s->hout[k];
+        return PIL_OK;
+    }
     st = pil_finalize(gs, n_global, p, s->dout, s->s_comp);
     if (st != PIL_OK) return st;
     PIL_TRY(cudaMemcpyAsync(s->hout, s->dout, sizeof(float) * PIL_NOUT, cudaMemcpyDeviceToHost, s->s_comp));
@@ -181,5 +203,17 @@ int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void*
     for (int k = 0; k < PIL_NOUT; ++k) loss_out_host[k] = s->hout[k];
     return PIL_OK;
 }
+
+int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B, int x_kind,
+                    const PilParams* p, float* loss_out_host) {
+    return session_run_impl(s, x_host, t_host, grad_host, B, x_kind, p, loss_out_host, 0);
+}
+
+int pil_session_run_ex(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B, int x_kind,
+                       const PilParams* p, float* loss_out_host, int flags) {
+    return session_run_impl(s, x_host, t_host, grad_host, B, x_kind, p, loss_out_host, flags);
+}
+
+void* pil_session_grad_ptr(PilSession* s) { return s ? s->dg : nullptr; }
 
 }  // extern "C"

@@ -7,12 +7,12 @@ from __future__ import annotations
 
 import ctypes
 from dataclasses import dataclass, replace
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib
-from ._lib import F32, BF16, U8, X_PROB, X_LOGITS_SIGMOID, X_LOGITS_TANH, PIL_NOUT, PIL_NSUMS, PilParams
+from ._lib import F32, BF16, U8, X_PROB, X_LOGITS_SIGMOID, X_LOGITS_TANH, PIL_NMOMENTS, PIL_NOUT, PIL_NSUMS, PilParams
 
 OUT_TOTAL, OUT_DICE, OUT_BCE, OUT_RD, OUT_PF, OUT_INVALID = 0, 1, 2, 3, 4, 5
 
@@ -146,6 +146,52 @@ def forward_sums(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, sum
                            _stream_ptr(dev))
     _lib.check(st, "pil_forward")
     return sums, (report if finalize else None)
+
+
+def forward_moments(x: torch.Tensor, t: torch.Tensor, kind: int, moments: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One pass over the maps -> the 13 parameter-independent sums (float64[16]) every loss setting is a
+    closed form of (include/pil.h pil_forward_moments).  All-reduce (SUM) across ranks when sharded."""
+    B, H, W = check_maps(x, t)
+    dev = x.device
+    if moments is None:
+        moments = torch.empty(PIL_NMOMENTS, dtype=torch.float64, device=dev)
+    ws = workspace(dev, B, H, W)
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_forward_moments(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                                            moments.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(st, "pil_forward_moments")
+    return moments
+
+
+def sweep_finalize(moments: torch.Tensor, n_global: int, params: Sequence[LossParams],
+                   reports: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Loss reports (float32[K, 8], rows laid out like finalize_report) of K parameter settings from one
+    moments vector; no pass over the maps."""
+    K = len(params)
+    if K < 1:
+        raise ValueError("need at least one parameter setting")
+    for p in params:
+        p.validate()
+    dev = moments.device
+    if reports is None:
+        reports = torch.empty(K, PIL_NOUT, dtype=torch.float32, device=dev)
+    arr = (PilParams * K)(*[p.c() for p in params])
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_sweep_finalize(moments.data_ptr(), int(n_global), arr, K, reports.data_ptr(), _stream_ptr(dev))
+    _lib.check(st, "pil_sweep_finalize")
+    return reports
+
+
+def sweep_losses(x: torch.Tensor, t: torch.Tensor, params: Sequence[LossParams], kind: int = X_PROB, group=None) -> torch.Tensor:
+    """Batched loss evaluation of a parameter grid (reference run_ablation.py:159-224 S2/S3 grids; BASELINE
+    config 4): ONE read of x and t for all K settings.  With `group`, x and t are this rank's shard of the
+    batch and the moments are all-reduced, so every rank returns the losses of the global batch."""
+    moments = forward_moments(x.detach(), t.detach(), kind)
+    if group is not None:
+        import torch.distributed as dist
+
+        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+    return sweep_finalize(moments, -1, params)
 
 
 def finalize_report(sums: torch.Tensor, n_global: int, p: LossParams, report: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -50,12 +50,16 @@ class HostSession:
         self._h = ctypes.c_void_p()
         self.shape = (int(max_batch), int(height), int(width))
         self.x_dtype, self.t_dtype = x_dtype, t_dtype
+        self._device = int(device)
         st = _lib.lib().pil_session_create(ctypes.byref(self._h), int(device), *self.shape, x_dtype, t_dtype)
         _lib.check(st, "pil_session_create")
 
-    def run(self, x_host, t_host, params: LossParams, grad_host=None, activation: str = "sigmoid") -> np.ndarray:
+    def run(self, x_host, t_host, params: LossParams, grad_host=None, activation: str = "sigmoid",
+            grad_on_device: bool = False) -> np.ndarray:
         """One forward+backward.  Returns the loss report (float32[8]: total, dice, bce, rd, pf, ...);
-        the gradient w.r.t. x is written into grad_host when given."""
+        the gradient w.r.t. x is written into grad_host when given.  With grad_on_device=True (and no
+        grad_host) the backward runs too but the gradient stays on the device -- `device_gradient()` views
+        it -- the way a training step consumes it; only the report crosses back."""
         params.validate()
         if self._h is None:
             raise RuntimeError("session closed")
@@ -67,11 +71,27 @@ class HostSession:
             raise TypeError("dtype differs from the session's")
         out = np.zeros(_lib.PIL_NOUT, dtype=np.float32)
         cp = params.c()
-        st = _lib.lib().pil_session_run(self._h, _host_ptr(x_host), _host_ptr(t_host),
-                                        _host_ptr(grad_host) if grad_host is not None else None, int(B),
-                                        activation_kind(activation), ctypes.byref(cp), out.ctypes.data)
-        _lib.check(st, "pil_session_run")
+        flags = _lib.PIL_SESSION_GRAD_ON_DEVICE if (grad_on_device and grad_host is None) else 0
+        st = _lib.lib().pil_session_run_ex(self._h, _host_ptr(x_host), _host_ptr(t_host),
+                                           _host_ptr(grad_host) if grad_host is not None else None, int(B),
+                                           activation_kind(activation), ctypes.byref(cp), out.ctypes.data, flags)
+        _lib.check(st, "pil_session_run_ex")
+        self._last_B = int(B)
         return out
+
+    def device_gradient(self) -> torch.Tensor:
+        """The gradient the last run(grad_on_device=True) left on the device, as a (B,1,H,W) tensor view
+        (valid until the next run; clone it to keep it)."""
+        if self.x_dtype != _lib.F32:
+            raise TypeError("device_gradient() views float32 sessions only")
+        ptr = _lib.lib().pil_session_grad_ptr(self._h)
+        B, (H, W) = getattr(self, "_last_B", self.shape[0]), self.shape[1:]
+        n = B * H * W
+
+        class _Arr:  # __cuda_array_interface__ producer over the session's buffer
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+        return torch.as_tensor(_Arr(), device=torch.device("cuda", self._device)).view(B, 1, H, W)
 
     def close(self) -> None:
         if self._h is not None and self._h.value:

@@ -256,3 +256,24 @@ def test_emulated_two_rank_data_parallel(P, po, dev):
     assert rel_max(grads.cpu().numpy(), 2.0 * og) < TOL
     host = P.loss_report_from_sums(gs.cpu().tolist(), None, p)
     assert rel_scalar(host["loss"], comps[0]) < TOL
+
+
+def test_host_session_gradient_on_device(dev):
+    """pil_session_run_ex(PIL_SESSION_GRAD_ON_DEVICE): same loss report and the same gradient as the
+    host-gradient path, with only the report crossing back."""
+    import physics_informed_image_segmentation_b200 as P
+    from tests.helpers import iid_inputs
+
+    z, t = iid_inputs(5, 48, 64, seed=9)
+    p = P.LossParams(pde_weight=1e-4, phase_field_weight=1e-4, diffusion_coeff=5.0)
+    zh, th = z.pin_memory(), t.pin_memory()
+    gh = torch.empty_like(zh).pin_memory()
+    with P.HostSession(5, 48, 64, device=0) as sess:
+        rep_h = sess.run(zh, th, p, grad_host=gh)
+        rep_d = sess.run(zh, th, p, grad_on_device=True)
+        gd = sess.device_gradient().clone()
+    torch.cuda.synchronize()
+    assert np.allclose(rep_d[:5], rep_h[:5], rtol=2e-6, atol=0)
+    assert gd.shape == (5, 1, 48, 64)
+    den = gh.abs().max().item()
+    assert (gd.cpu() - gh).abs().max().item() / den < 2e-6
