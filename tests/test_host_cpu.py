@@ -162,3 +162,68 @@ def test_install_into_reference_rebinds_names():
     with P.use_logits_head(m) as name:
         assert name == "sigmoid" and m.activation_name == "none"
     assert m.activation_name == "sigmoid"
+
+
+def test_exchange_descriptor_layout_and_validation():
+    """PilExchange is a plain struct shared with C: its layout must match include/pil.h, and a bad
+    descriptor is rejected before any CUDA call."""
+    L = _lib.lib()
+    assert ctypes.sizeof(_lib.PilExchange) == 4 + 4 + 8 + 4 + 4 + 8 * _lib.PIL_MAX_RANKS
+    assert _lib.PilExchange.mailbox.offset == 24
+    text = open(os.path.join(ROOT, "include", "pil.h")).read()
+    assert f"#define PIL_MAX_RANKS {_lib.PIL_MAX_RANKS}" in text
+    assert f"#define PIL_IPC_HANDLE_BYTES {_lib.PIL_IPC_HANDLE_BYTES}" in text
+    assert f"#define PIL_NMOMENTS {_lib.PIL_NMOMENTS}" in text
+    assert L.pil_exchange_bytes() >= 2 * 2 * _lib.PIL_MAX_RANKS * 128 + 4
+    ok = P.LossParams().c()
+    wsb = L.pil_workspace_bytes(1, 8, 8)
+    buf = (ctypes.c_char * wsb)()
+    a = ctypes.addressof(buf)
+    ex = _lib.PilExchange()
+    ex.rank, ex.world, ex.epoch = 0, 2, 0          # mailbox pointers NULL
+    assert L.pil_forward_pointwise_xchg(a, a, 1, 8, 8, 0, 0, 1, ctypes.byref(ok), a, a, wsb, ctypes.byref(ex), None) == -11
+    ex.rank, ex.world = 3, 2                       # rank out of range
+    ex.mailbox[0] = a
+    ex.mailbox[1] = a
+    assert L.pil_forward_pointwise_xchg(a, a, 1, 8, 8, 0, 0, 1, ctypes.byref(ok), a, a, wsb, ctypes.byref(ex), None) == -11
+    ex.rank, ex.world = 0, _lib.PIL_MAX_RANKS + 1  # more ranks than a mailbox has slots for
+    assert L.pil_exchange_finalize(ctypes.byref(ex), -1, ctypes.byref(ok), a, a, None) == -11
+    assert L.pil_forward_pointwise_xchg(a, a, 1, 8, 8, 0, 0, 1, ctypes.byref(ok), a, a, wsb, None, None) == -1
+
+
+def test_sweep_grids_match_reference_definitions():
+    """s2_grid / s3_grid restate run_ablation.py:159-224; checked against the live definitions when the
+    reference checkout is present (build container), against the documented values otherwise."""
+    s2, s3 = P.s2_grid(), P.s3_grid()
+    assert [p.diffusion_coeff for p in s2] == [0.5, 1.0, 2.0, 5.0, 10.0, 100.0]
+    assert all(p.pde_weight == 1e-3 and p.phase_field_weight == 0.0 for p in s2)
+    assert [p.epsilon for p in s3] == [0.001, 0.01, 0.05, 0.1, 0.2]
+    assert all(p.pde_weight == 1e-4 and p.phase_field_weight == 1e-4 and p.diffusion_coeff == 5.0
+               and p.reaction_threshold == 0.5 for p in s3)
+    ref = "/root/reference/run_ablation.py"
+    if os.path.exists(ref):
+        src = open(ref).read()
+        assert "for i, d in enumerate([0.5, 1.0, 2.0, 5.0, 10.0, 100.0])" in src
+        assert "for i, eps in enumerate([0.001, 0.01, 0.05, 0.1, 0.2])" in src
+    # sweep_finalize validates every setting before touching the device
+    with pytest.raises(ValueError, match="reaction_threshold must be in"):
+        Fn.sweep_finalize(torch.zeros(16, dtype=torch.float64), 1, [P.LossParams(reaction_threshold=0.0)])
+
+
+def test_sweep_closed_form_matches_direct_evaluation():
+    """The algebra behind pil_sweep_finalize, on the CPU with the oracle: sum r^2 for any (D, a) from the six
+    second moments of {lap, g, h} equals the oracle's direct sum (fp64)."""
+    from oracle import pil_oracle as po
+
+    rng = np.random.default_rng(0)
+    u = rng.random((2, 1, 17, 23))
+    t = (rng.random((2, 1, 17, 23)) > 0.5).astype(np.float64)
+    up = np.pad(u, ((0, 0), (0, 0), (1, 1), (1, 1)), mode="reflect")
+    lap = up[..., 2:, 1:-1] + up[..., :-2, 1:-1] + up[..., 1:-1, 2:] + up[..., 1:-1, :-2] - 4.0 * u
+    g = u * (1.0 - u)
+    h = g * u
+    for D, a in [(0.5, 0.5), (5.0, 0.3), (100.0, 0.7)]:
+        closed = (D * D * (lap * lap).sum() + 2 * D * (lap * h).sum() - 2 * a * D * (lap * g).sum() + (h * h).sum()
+                  - 2 * a * (h * g).sum() + a * a * (g * g).sum())
+        s = po.sums(u, t, po.Params(diffusion_coeff=D, reaction_threshold=a), po.X_PROB)
+        assert abs(closed - s[4]) / s[4] < 1e-12
