@@ -375,3 +375,63 @@ def test_retained_graph_second_backward(dev, po):
     assert rel_max(x.grad.cpu().numpy(), 2.0 * g1.cpu().numpy()) < 2e-6
     comps, og = po.loss_and_grad(z.numpy().astype(np.float64), t.numpy().astype(np.float64), po.STAGE2, 1)
     assert rel_max(g1.cpu().numpy(), og) < TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# dynamic range claiming of the accumulating backward (persistent grid + global task counter)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,kind,rows", [((3, 127, 1024), 1, 8), ((2, 70, 360), 1, 9), ((5, 64, 248), 0, 16),
+                                             ((1, 300, 132), 2, 64), ((4, 33, 52), 1, 1000)])
+def test_dynamic_claiming_small_ranges_vs_oracle(Fn, po, dev, shape, kind, rows):
+    """Force short dynamically claimed ranges (many tasks per warp, ranges straddling image boundaries) on
+    shapes small enough for the oracle: loss report and gradient of the training-step split must match."""
+    from physics_informed_image_segmentation_b200 import _lib
+
+    B, H, W = shape
+    z, t = blob_inputs(B, H, W, seed=21)
+    if kind == 0:
+        z = torch.sigmoid(z)
+    x, tt, p = z.to(dev), t.to(dev), lp(Fn, po.STAGE2)
+    try:
+        _lib.lib().pil_set_tuning(0, rows)
+        rep, sums, g = Fn.loss_fwd_bwd(x, tt, p, kind)
+        info = Fn.launch_info()
+        rep2, sums2, g2 = Fn.loss_fwd_bwd(x, tt, p, kind)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().pil_set_tuning(0, 0)
+    assert info.bwd_rows_per_segment <= max(rows, 8)
+    z64, t64 = z.numpy().astype(np.float64), t.numpy().astype(np.float64)
+    comps, og = po.loss_and_grad(z64, t64, po.STAGE2, kind)
+    for k in range(5):
+        assert rel_scalar(rep[k].item(), comps[k]) < TOL, (k, rep[k].item(), comps[k])
+    assert rel_max(g.cpu().numpy(), og) < TOL and rel_l2(g.cpu().numpy(), og) < TOL
+    # which warp takes which range changes from run to run: the gradient must not, the sums only in fp64 rounding
+    assert torch.equal(g, g2)
+    assert torch.allclose(sums, sums2, rtol=1e-12, atol=0)
+
+
+def test_full_size_dynamic_step_matches_static_kernels(Fn, po, dev):
+    """64 x 1024 x 1024: the training-step split (pointwise forward + dynamically scheduled accumulating
+    backward) against the statically partitioned full forward / plain backward on the same maps."""
+    B, H, W = 64, 1024, 1024
+    g = torch.Generator(device=dev).manual_seed(78)
+    z = 2.0 * torch.randn(B, 1, H, W, device=dev, generator=g)
+    t = (torch.rand(B, 1, H, W, device=dev, generator=g) > 0.5).float()
+    p = lp(Fn, po.STAGE2)
+    rep, sums, grad = Fn.loss_fwd_bwd(z, t, p, 1)
+    info = Fn.launch_info()
+    assert info.bwd_rows_per_segment == 64 and info.bwd_blocks <= 4 * 148  # persistent grid, 64-row ranges
+    s_ref, r_ref = Fn.forward_sums(z, t, p, 1)
+    g_ref = Fn.backward_grad(z, t, p, 1, s_ref, z.numel())
+    for k in range(5):
+        assert rel_scalar(rep[k].item(), r_ref[k].item()) < 2e-6
+    assert torch.allclose(sums[:6], s_ref[:6], rtol=2e-6, atol=0) and sums[7] == s_ref[7]
+    assert rel_max(grad.cpu().numpy(), g_ref.cpu().numpy()) < 2e-6
+    rep2, sums2, grad2 = Fn.loss_fwd_bwd(z, t, p, 1)
+    assert torch.equal(grad, grad2) and torch.allclose(sums, sums2, rtol=1e-12, atol=0)
+    # oracle on an 8-image slice, with the global sums
+    sl = slice(56, 64)
+    og = po.backward(z[sl].cpu().numpy().astype(np.float64), t[sl].cpu().numpy().astype(np.float64), po.STAGE2,
+                     sums.cpu().numpy(), z.numel(), 1)
+    assert rel_max(grad[sl].cpu().numpy(), og) < TOL
