@@ -82,6 +82,8 @@ typedef struct PilParams {
     double smooth;
 } PilParams;
 
+struct PilExchange; /* peer-memory exchange descriptor, defined below */
+
 int pil_version(void);
 const char* pil_status_string(int status);
 
@@ -170,6 +172,27 @@ int pil_loss_fwd_bwd(const void* x, const void* t, void* grad, int64_t B, int64_
                      int x_dtype, int t_dtype, int x_kind, const PilParams* p,
                      double* sums, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
 int pil_scale_gradient(void* grad, int dtype, int64_t n, const float* upstream, void* stream);
+
+/*
+ * Per-step accuracy metrics folded into the step.  train_epoch / validate compute, between
+ * forward and backward, the per-image Dice and IoU of the prediction thresholded at 0.5
+ * (src/train.py:153-160 -> src/metrics.py:38-73 compute_dice_score_batch, src/evaluate.py:62-97
+ * compute_iou_batch: B Python iterations of ~6 kernels each).  pil_forward_pointwise_metrics IS the
+ * pointwise forward (same sums, same exchange push when ex != NULL) and, on the same read of x and t, also
+ * leaves three counts per image:
+ *   image_counts (device, B x 4 doubles, zeroed by the call): [b][0] sum [u > threshold]*t
+ *   [b][1] sum [u > threshold]   [b][2] sum t   [b][3] 0
+ * pil_image_metrics turns them into dice[b] = (2I+s)/(P+T+s) and iou[b] = (I+s)/(P+T-I+s) on the device
+ * (either output may be NULL).  The boundary-F1 of src/evaluate.py:125-229 (OpenCV contours + distance
+ * transform on the host) is not part of this path.
+ */
+int pil_forward_pointwise_metrics(const void* x, const void* t, int64_t B, int64_t H, int64_t W,
+                                  int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                                  double* sums, double* image_counts, float threshold,
+                                  void* workspace, size_t workspace_bytes,
+                                  const struct PilExchange* ex /* may be NULL */, void* stream);
+int pil_image_metrics(const double* image_counts, int64_t B, double smooth,
+                      float* dice_out, float* iou_out, void* stream);
 
 /*
  * Parameter sweeps (BASELINE config 4; the S2/S3 sensitivity grids of run_ablation.py:159-224 evaluated as

@@ -99,6 +99,12 @@ _SIGS = {
     "pil_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PilParams),
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "pil_forward_pointwise_metrics": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PilParams),
+                                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
+                                                     ctypes.c_size_t, ctypes.POINTER(PilExchange), ctypes.c_void_p]),
+    "pil_image_metrics": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
     "pil_forward_moments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_size_t, ctypes.c_void_p]),

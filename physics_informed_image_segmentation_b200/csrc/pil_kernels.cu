@@ -1059,6 +1059,132 @@ __global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const Point
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1M: pointwise forward + per-image thresholded counts (pil_forward_pointwise_metrics).
+// The per-step accuracy metrics of the reference (per-image Dice and IoU of the map thresholded at 0.5,
+// src/train.py:153-160 -> src/metrics.py:38-73, src/evaluate.py:62-97) need three counts per image:
+//   sum [u > thr]*t,  sum [u > thr],  sum t.
+// They ride on the pass that already reads x and t.  Unlike K1L every block walks ONE contiguous piece of
+// the shard, image by image, so a block flushes its counts once per image it touches (<= 3 atomics per
+// warp) instead of once per iteration.
+// ------------------------------------------------------------------------------------------------
+struct PointMetricsArgs {
+    const void* x;
+    const void* t;
+    long long n;    // pixels in the shard
+    long long hw;   // pixels per image
+    double* partials;
+    unsigned int* ticket;
+    double* sums;
+    PilParams p;
+    double* image_counts;  // [B][4], zero on entry
+    float threshold;
+    XchgDev X;
+};
+
+template <int KIND, typename XT, typename TT, bool ALIGNED>
+__global__ void __launch_bounds__(kPointThreads, 3) pil_point_metrics_kernel(const PointMetricsArgs A) {
+    pdl_wait();
+    pdl_launch_dependents();
+    FwdRow<KIND, true> fr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fr.acc[k] = 0.f;
+    fr.init_packed();
+    const XT* x = reinterpret_cast<const XT*>(A.x);
+    const TT* t = reinterpret_cast<const TT*>(A.t);
+    const float thr = A.threshold;
+    constexpr int V = ALIGNED ? 4 : 1;                      // pixels per unit of work
+    const long long units = A.n / V, hwu = A.hw / V;        // ALIGNED: n % 4 == 0 and hw % 4 == 0
+    const long long c0 = (units * (long long)blockIdx.x) / gridDim.x, c1 = (units * ((long long)blockIdx.x + 1)) / gridDim.x;
+    const int lane = threadIdx.x & 31;
+    for (long long img = c0 / hwu; img * hwu < c1; ++img) {
+        const long long lo = max(c0, img * hwu), hi = min(c1, (img + 1) * hwu);
+        f2 cI = make_float2(0.f, 0.f), cP = make_float2(0.f, 0.f);
+        const f2 T0 = fr.pa[2];
+        auto count2 = [&](f2 u, f2 tt) {
+            const f2 pb = make_float2(u.x > thr ? 1.0f : 0.0f, u.y > thr ? 1.0f : 0.0f);  // src/metrics.py:58
+            cP = add2(cP, pb);
+            cI = fma2(pb, tt, cI);
+        };
+        if constexpr (ALIGNED) {
+            long long i = lo + threadIdx.x;
+            constexpr long long S = kPointThreads;
+            for (; i < hi; i += kPointUnroll * S) {
+                float4 xv[kPointUnroll], tv[kPointUnroll];
+#pragma unroll
+                for (int q = 0; q < kPointUnroll; ++q) {
+                    if (i + q * S < hi) {
+                        xv[q] = ld4<XT>(x + 4 * (i + q * S));
+                        tv[q] = ld4<TT>(t + 4 * (i + q * S));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kPointUnroll; ++q) {
+                    if (i + q * S < hi) {
+                        const float4 u4 = fr.point4(xv[q], tv[q], true);
+                        count2(make_float2(u4.x, u4.y), make_float2(tv[q].x, tv[q].y));
+                        count2(make_float2(u4.z, u4.w), make_float2(tv[q].z, tv[q].w));
+                    }
+                }
+            }
+        } else {
+            // scalar path: every pixel is evaluated as the pair (px, px); the loss sums are halved at the end
+            for (long long i = lo + threadIdx.x; i < hi; i += kPointThreads) {
+                const float xs = ld1<XT>(x + i), ts = ld1<TT>(t + i);
+                const f2 u = fr.point2(make_float2(xs, xs), make_float2(ts, ts), true);
+                const float pb = u.x > thr ? 1.0f : 0.0f;
+                cP.x += pb;
+                cI.x = fmaf(pb, ts, cI.x);
+            }
+        }
+        float vI = cI.x + cI.y, vP = cP.x + cP.y;
+        float vT = (fr.pa[2].x - T0.x) + (fr.pa[2].y - T0.y);
+        if constexpr (!ALIGNED) vT *= 0.5f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vI += __shfl_xor_sync(0xffffffffu, vI, o);
+            vP += __shfl_xor_sync(0xffffffffu, vP, o);
+            vT += __shfl_xor_sync(0xffffffffu, vT, o);
+        }
+        if (lane == 0) {
+            atomicAdd(A.image_counts + img * 4 + 0, (double)vI);
+            atomicAdd(A.image_counts + img * 4 + 1, (double)vP);
+            atomicAdd(A.image_counts + img * 4 + 2, (double)vT);
+        }
+    }
+    fr.fold_packed();
+    if constexpr (!ALIGNED) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fr.acc[k] *= 0.5f;
+    }
+    double raw[PIL_NSUMS];
+    if (!reduce_to_last_block<kPointThreads, float>(fr.acc, A.partials, A.ticket, raw)) return;
+    __shared__ double s_push[PIL_NSUMS];
+    if (threadIdx.x == 0) {
+        double sv[PIL_NSUMS];
+        sums_from_raw(raw, A.p.epsilon, (double)A.n, sv);
+#pragma unroll
+        for (int k = 0; k < PIL_NSUMS; ++k) {
+            A.sums[k] = sv[k];
+            s_push[k] = sv[k];
+        }
+        *A.ticket = 0u;
+    }
+    if (A.X.world > 0) {
+        __syncthreads();
+        xchg_push(A.X, 0, s_push);
+    }
+}
+
+// per-image Dice and IoU from the counts (src/metrics.py:66-70, src/evaluate.py:90-94)
+__global__ void pil_image_metrics_kernel(const double* counts, long long B, double smooth, float* dice, float* iou) {
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const double I = counts[4 * b], P = counts[4 * b + 1], T = counts[4 * b + 2];
+        if (dice) dice[b] = (float)((2.0 * I + smooth) / (P + T + smooth));
+        if (iou) iou[b] = (float)((I + smooth) / (P + T - I + smooth));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: fused backward
 // ------------------------------------------------------------------------------------------------
 struct BwdCoef {
@@ -2062,6 +2188,41 @@ __global__ void __launch_bounds__(256) pil_scale_kernel_generic(void* __restrict
     }
 }
 
+template <int KIND, typename XT, typename TT>
+static cudaError_t launch_point_metrics_a(const PointMetricsArgs& a, bool aligned, cudaStream_t s, int* blocks_out) {
+    const long long units = aligned ? (a.n >> 2) : a.n;
+    long long blocks = (units + (long long)kPointThreads * kPointUnroll - 1) / ((long long)kPointThreads * kPointUnroll);
+    const long long cap = (long long)sm_count() * 3;
+    if (blocks > cap) blocks = cap;
+    if (blocks > kMaxPointBlocks) blocks = kMaxPointBlocks;
+    if (blocks < 1) blocks = 1;
+    *blocks_out = (int)blocks;
+    if (aligned) return launch_pdl(pil_point_metrics_kernel<KIND, XT, TT, true>, (int)blocks, kPointThreads, 0, s, a);
+    return launch_pdl(pil_point_metrics_kernel<KIND, XT, TT, false>, (int)blocks, kPointThreads, 0, s, a);
+}
+template <int KIND, typename XT>
+static cudaError_t launch_point_metrics_t(int t_dtype, const PointMetricsArgs& a, bool aligned, cudaStream_t s, int* b) {
+#ifdef PIL_DEV_F32_ONLY
+    if (t_dtype != PIL_F32) return cudaErrorNotSupported;
+    return launch_point_metrics_a<KIND, XT, float>(a, aligned, s, b);
+#else
+    switch (t_dtype) {
+        case PIL_F32: return launch_point_metrics_a<KIND, XT, float>(a, aligned, s, b);
+        case PIL_BF16: return launch_point_metrics_a<KIND, XT, __nv_bfloat16>(a, aligned, s, b);
+        default: return launch_point_metrics_a<KIND, XT, uint8_t>(a, aligned, s, b);
+    }
+#endif
+}
+template <int KIND>
+static cudaError_t launch_point_metrics_x(int x_dtype, int t_dtype, const PointMetricsArgs& a, bool aligned, cudaStream_t s, int* b) {
+    if (x_dtype == PIL_F32) return launch_point_metrics_t<KIND, float>(t_dtype, a, aligned, s, b);
+#ifdef PIL_DEV_F32_ONLY
+    return cudaErrorNotSupported;
+#else
+    return launch_point_metrics_t<KIND, __nv_bfloat16>(t_dtype, a, aligned, s, b);
+#endif
+}
+
 struct WorkspaceLayout {
     size_t ticket_off, scratch_off, partials_off, total;
 };
@@ -2389,6 +2550,54 @@ int pil_backward_accumulate_xchg(const void* x, const void* t, void* grad, int64
     }
     return backward_impl(x, t, grad, B, H, W, x_dtype, t_dtype, x_kind, p, nullptr, n_global, upstream, grad_scale,
                          stencil_sums, loss_out, total_sums, workspace, stream, ex);
+}
+
+int pil_forward_pointwise_metrics(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                                  int x_kind, const PilParams* p, double* sums, double* image_counts, float threshold,
+                                  void* workspace, size_t workspace_bytes, const PilExchange* ex, void* stream) {
+    int st = check_common(x, t, B, H, W, x_dtype, t_dtype, x_kind, p);
+    if (st != PIL_OK) return st;
+    if (!sums || !workspace || !image_counts) return PIL_ERR_NULL;
+    const WorkspaceLayout wl = workspace_layout(B, H, W);
+    if (workspace_bytes < wl.total || ((uintptr_t)workspace % 8) || ((uintptr_t)image_counts % 8)) return PIL_ERR_WORKSPACE;
+    PointMetricsArgs a;
+    a.x = x;
+    a.t = t;
+    a.n = (long long)B * H * W;
+    a.hw = (long long)H * W;
+    a.ticket = reinterpret_cast<unsigned int*>((char*)workspace + wl.ticket_off);
+    a.partials = reinterpret_cast<double*>((char*)workspace + wl.partials_off);
+    a.sums = sums;
+    a.p = *p;
+    a.image_counts = image_counts;
+    a.threshold = threshold;
+    st = make_xchg(ex, &a.X);
+    if (st != PIL_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(image_counts, 0, (size_t)B * 4 * sizeof(double), s);
+    if (e != cudaSuccess) return (int)e;
+    const bool aligned = (a.hw % 4 == 0) && is_aligned_case(x, t, nullptr, 4, x_dtype, t_dtype);
+    int blocks = 0;
+    switch (x_kind) {
+        case PIL_X_PROB: e = launch_point_metrics_x<PIL_X_PROB>(x_dtype, t_dtype, a, aligned, s, &blocks); break;
+        case PIL_X_LOGITS_SIGMOID: e = launch_point_metrics_x<PIL_X_LOGITS_SIGMOID>(x_dtype, t_dtype, a, aligned, s, &blocks); break;
+        default: e = launch_point_metrics_x<PIL_X_LOGITS_TANH>(x_dtype, t_dtype, a, aligned, s, &blocks); break;
+    }
+    t_info.fwd_blocks = blocks;
+    t_info.fwd_threads = kPointThreads;
+    t_info.fwd_rows_per_segment = 0;
+    t_info.fwd_aligned = aligned ? 1 : 0;
+    ++g_kernels_launched;
+    return (int)e;
+}
+
+int pil_image_metrics(const double* image_counts, int64_t B, double smooth, float* dice_out, float* iou_out, void* stream) {
+    if (!image_counts || (!dice_out && !iou_out)) return PIL_ERR_NULL;
+    if (B < 1) return PIL_ERR_SHAPE;
+    const int blocks = (int)((B + 127) / 128 < 64 ? (B + 127) / 128 : 64);
+    pil_image_metrics_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(image_counts, (long long)B, smooth, dice_out, iou_out);
+    ++g_kernels_launched;
+    return (int)cudaGetLastError();
 }
 
 int pil_exchange_finalize(const PilExchange* ex, int64_t n_global, const PilParams* p, float* loss_out, double* total_sums,

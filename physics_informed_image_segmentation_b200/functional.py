@@ -274,6 +274,42 @@ def backward_accumulate(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: i
     return out, stencil_sums
 
 
+def forward_pointwise_metrics(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, threshold: float = 0.5,
+                              sums: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+                              ex: Optional["_lib.PilExchange"] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1M: the pointwise forward plus, on the same read of x and t, three counts per image
+    (float64[B, 4]: sum [u>thr]*t, sum [u>thr], sum t, 0) -- what the reference's per-step Dice/IoU metrics
+    need (src/metrics.py:38-73, src/evaluate.py:62-97).  Returns (sums, counts)."""
+    B, H, W = check_maps(x, t)
+    dev = x.device
+    if sums is None:
+        sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+    if counts is None:
+        counts = torch.empty(B, 4, dtype=torch.float64, device=dev)
+    ws = workspace(dev, B, H, W)
+    cp = p.c()
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_forward_pointwise_metrics(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                                                      ctypes.byref(cp), sums.data_ptr(), counts.data_ptr(), float(threshold),
+                                                      ws.data_ptr(), ws.numel(), ctypes.byref(ex) if ex is not None else None,
+                                                      _stream_ptr(dev))
+    _lib.check(st, "pil_forward_pointwise_metrics")
+    return sums, counts
+
+
+def image_metrics(counts: torch.Tensor, smooth: float = 1e-6) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(dice[B], iou[B]) float32 from the per-image counts, on the device (src/metrics.py:66-70,
+    src/evaluate.py:90-94)."""
+    B = counts.shape[0]
+    dev = counts.device
+    dice = torch.empty(B, dtype=torch.float32, device=dev)
+    iou = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_image_metrics(counts.data_ptr(), B, float(smooth), dice.data_ptr(), iou.data_ptr(), _stream_ptr(dev))
+    _lib.check(st, "pil_image_metrics")
+    return dice, iou
+
+
 def forward_pointwise_xchg(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, ex: "_lib.PilExchange",
                            sums: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K1L + push of the shard's sums into every rank's mailbox (include/pil.h pil_forward_pointwise_xchg)."""
@@ -404,10 +440,25 @@ class _FusedLossFn(torch.autograd.Function):
     serves the total loss AND the four logged components (reference src/train.py:120-150)."""
 
     @staticmethod
-    def forward(ctx, x, t, p: LossParams, kind: int, which: int, group, ddp_average: bool):
+    def forward(ctx, x, t, p: LossParams, kind: int, which: int, group, ddp_average: bool, metrics_thr=None):
         x_d = x.detach()
         t_d = t.detach()
         pg = _params_for(p, which)  # the gradient is that of the requested entry
+        counts = None
+        if metrics_thr is not None and group is None:
+            # per-image threshold counts ride on the pointwise forward (K1M), then the usual backward
+            sums, counts = forward_pointwise_metrics(x_d, t_d, pg, kind, metrics_thr)
+            report = torch.empty(PIL_NOUT, dtype=torch.float32, device=x_d.device)
+            stencil = torch.empty(PIL_NSUMS, dtype=torch.float64, device=x_d.device)
+            grad, _ = backward_accumulate(x_d, t_d, pg, kind, sums, x_d.numel(), stencil_sums=stencil, report=report)
+            sums = sums + stencil
+            if pg is not p:
+                report = finalize_report(sums, x_d.numel(), p)
+            ctx.save_for_backward(x_d, t_d, sums)
+            ctx.grad = grad
+            ctx.p, ctx.kind, ctx.n_global, ctx.scale = pg, kind, x_d.numel(), 1.0
+            ctx.mark_non_differentiable(report, counts)
+            return report[which], report, counts
         if group is not None:
             import torch.distributed as dist
 
@@ -418,14 +469,22 @@ class _FusedLossFn(torch.autograd.Function):
             if px is not None and pg is p:
                 # peer-memory path: the two kernels swap their sums over NVLink themselves (no NCCL call)
                 ex = px.next_step()
-                forward_pointwise_xchg(x_d, t_d, pg, kind, ex)
+                if metrics_thr is not None:
+                    _, counts = forward_pointwise_metrics(x_d, t_d, pg, kind, metrics_thr, ex=ex)
+                else:
+                    forward_pointwise_xchg(x_d, t_d, pg, kind, ex)
                 grad, report, sums = backward_accumulate_xchg(x_d, t_d, pg, kind, ex, -1, grad_scale=scale)
                 ctx.save_for_backward(x_d, t_d, sums)
                 ctx.grad = grad
                 ctx.p, ctx.kind, ctx.n_global, ctx.scale = pg, kind, -1, scale
-                ctx.mark_non_differentiable(report)
-                return report[which], report
-            sums = forward_pointwise(x_d, t_d, pg, kind)
+                if counts is None:
+                    counts = torch.empty(0, 4, dtype=torch.float64, device=x_d.device)
+                ctx.mark_non_differentiable(report, counts)
+                return report[which], report, counts
+            if metrics_thr is not None:
+                sums, counts = forward_pointwise_metrics(x_d, t_d, pg, kind, metrics_thr)
+            else:
+                sums = forward_pointwise(x_d, t_d, pg, kind)
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)           # the gradient needs global I, P, T
             grad, stencil = backward_accumulate(x_d, t_d, pg, kind, sums, -1, grad_scale=scale)
             dist.all_reduce(stencil, op=dist.ReduceOp.SUM, group=group)        # only the loss VALUE needs these
@@ -440,19 +499,38 @@ class _FusedLossFn(torch.autograd.Function):
         ctx.save_for_backward(x_d, t_d, sums)
         ctx.grad = grad
         ctx.p, ctx.kind, ctx.n_global, ctx.scale = pg, kind, n_global, scale
-        ctx.mark_non_differentiable(report)
-        return report[which], report
+        if counts is None:
+            counts = torch.empty(0, 4, dtype=torch.float64, device=x_d.device)
+        ctx.mark_non_differentiable(report, counts)
+        return report[which], report, counts
 
     @staticmethod
-    def backward(ctx, g_loss, _g_report):
+    def backward(ctx, g_loss, _g_report, _g_counts):
         grad = ctx.grad
         if grad is not None:
             ctx.grad = None  # the buffer is scaled in place, so it can be handed out once
-            return scale_gradient(grad, g_loss), None, None, None, None, None, None
+            return scale_gradient(grad, g_loss), None, None, None, None, None, None, None
         # second backward through a retained graph: recompute from the saved global sums
         x, t, sums = ctx.saved_tensors
         grad = backward_grad(x, t, ctx.p, ctx.kind, sums, ctx.n_global, upstream=g_loss, grad_scale=ctx.scale)
-        return grad, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None
+
+
+def fused_loss_with_counts(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int = X_PROB, which: int = OUT_TOTAL,
+                           group=None, ddp_average: bool = True, metrics_threshold: Optional[float] = None):
+    """(requested scalar with grad_fn, detached report float32[8], per-image counts float64[B,4] or None).
+    With metrics_threshold the per-image threshold counts of this rank's images come from the same pass
+    over the maps in the training path; the no-grad path spends one extra pointwise pass on them."""
+    p.validate()
+    check_maps(x, t)
+    if x.requires_grad and torch.is_grad_enabled():
+        loss, report, counts = _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average, metrics_threshold)
+        return loss, report, (counts if metrics_threshold is not None else None)
+    loss, report = fused_loss(x, t, p, kind, which, group, ddp_average)
+    counts = None
+    if metrics_threshold is not None:
+        _, counts = forward_pointwise_metrics(x.detach(), t.detach(), p, kind, metrics_threshold)
+    return loss, report, counts
 
 
 def fused_loss(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int = X_PROB, which: int = OUT_TOTAL,
@@ -461,7 +539,8 @@ def fused_loss(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int = X_PR
     p.validate()
     check_maps(x, t)
     if x.requires_grad and torch.is_grad_enabled():
-        return _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average)
+        loss, report, _ = _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average, None)
+        return loss, report
     # no graph needed (validation / logging): skip the autograd.Function overhead
     if group is not None:
         import torch.distributed as dist

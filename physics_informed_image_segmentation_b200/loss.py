@@ -48,14 +48,20 @@ class _FusedLossBase(nn.Module):
         self.ddp_average = ddp_average
         self._last = None  # (key, report) of the most recent fused forward
         self.last_report: Optional[torch.Tensor] = None
+        # Per-step accuracy metrics (reference src/train.py:153-160): set to a threshold (0.5 in the
+        # reference) to have every forward also leave per-image threshold counts; None = off.
+        self.batch_metrics_threshold: Optional[float] = None
+        self._last_counts: Optional[torch.Tensor] = None
 
     def _params(self) -> LossParams:
         raise NotImplementedError
 
     def _run(self, x: torch.Tensor, t: torch.Tensor, kind: int) -> torch.Tensor:
         p = self._params()
-        loss, report = Fn.fused_loss(x, t, p, kind, Fn.OUT_TOTAL, self.process_group, self.ddp_average)
+        loss, report, counts = Fn.fused_loss_with_counts(x, t, p, kind, Fn.OUT_TOTAL, self.process_group, self.ddp_average,
+                                                         self.batch_metrics_threshold)
         self.last_report = report
+        self._last_counts = counts
         # identity (weak) + version counter: a different tensor that merely reuses the address never hits
         self._last = (weakref.ref(x), x._version, weakref.ref(t), t._version, kind, p, report)
         return loss
@@ -81,6 +87,21 @@ class _FusedLossBase(nn.Module):
             raise RuntimeError("no forward pass has run yet")
         r = self.last_report
         return {"loss": r[0], "dice_loss": r[1], "bce_loss": r[2], "pde_loss": r[3], "phase_field_loss": r[4]}
+
+    def enable_batch_metrics(self, threshold: Optional[float] = 0.5) -> "_FusedLossBase":
+        """Have every forward also produce the reference's per-image Dice / IoU of the thresholded prediction
+        (compute_dice_score_batch, src/metrics.py:38-73; compute_iou_batch, src/evaluate.py:62-97) from
+        the same read of the maps; `None` switches it off."""
+        self.batch_metrics_threshold = threshold
+        return self
+
+    def last_batch_metrics(self, smooth: float = 1e-6) -> dict:
+        """{'dice': float32[B], 'iou': float32[B]} of this rank's images in the most recent forward
+        (device tensors, no sync) -- what src/train.py:155-156 computes with 2 x B Python iterations."""
+        if self._last_counts is None:
+            raise RuntimeError("no forward pass with batch metrics enabled has run yet (enable_batch_metrics())")
+        dice, iou = Fn.image_metrics(self._last_counts, smooth)
+        return {"dice": dice, "iou": iou}
 
     def forward(self, predictions: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         return self._run(predictions, targets, Fn.X_PROB)

@@ -277,3 +277,53 @@ def test_host_session_gradient_on_device(dev):
     assert gd.shape == (5, 1, 48, 64)
     den = gh.abs().max().item()
     assert (gd.cpu() - gh).abs().max().item() / den < 2e-6
+
+
+def _ref_dice_iou(u, t, thr=0.5, smooth=1e-6):
+    """reference src/metrics.py:38-73 and src/evaluate.py:62-97, restated with torch on the CPU"""
+    pb = (u > thr).float()
+    B = u.shape[0]
+    I = (pb * t).reshape(B, -1).double().sum(1)
+    P = pb.reshape(B, -1).double().sum(1)
+    T = t.reshape(B, -1).double().sum(1)
+    return ((2 * I + smooth) / (P + T + smooth)).float(), ((I + smooth) / (P + T - I + smooth)).float()
+
+
+@pytest.mark.parametrize("shape", [(6, 64, 96), (3, 33, 50), (2, 7, 9), (5, 256, 256)])
+@pytest.mark.parametrize("entry", ["prob", "logits"])
+def test_batch_metrics_ride_on_the_training_step(dev, shape, entry):
+    """Per-image thresholded Dice / IoU (reference train_epoch, src/train.py:153-160) from the same pass as the
+    loss: values match the reference formulas, and loss / gradient are unchanged by switching them on."""
+    import physics_informed_image_segmentation_b200 as P
+    from tests.helpers import blob_inputs
+
+    B, H, W = shape
+    z, t = blob_inputs(B, H, W, seed=31)
+    u = torch.sigmoid(z)
+    crit = P.DiceBCEPDELoss(pde_weight=1e-4, phase_field_weight=1e-4, diffusion_coeff=5.0).to(dev)
+
+    def run(metrics):
+        crit.enable_batch_metrics(0.5 if metrics else None)
+        x = (u if entry == "prob" else z).to(dev).requires_grad_(True)
+        loss = crit(x, t.to(dev)) if entry == "prob" else crit.forward_logits(x, t.to(dev))
+        loss.backward()
+        return loss.detach(), x.grad
+
+    l0, g0 = run(False)
+    l1, g1 = run(True)
+    m = crit.last_batch_metrics()
+    assert abs(l0.item() - l1.item()) <= 2e-6 * abs(l0.item())
+    assert (g0 - g1).abs().max().item() <= 2e-6 * g0.abs().max().item()
+    # the threshold is applied to the kernel's own fp32 u: compare against u as the GPU computes it for logits
+    u_ref = u if entry == "prob" else torch.sigmoid(z.to(dev)).cpu()
+    dice_ref, iou_ref = _ref_dice_iou(u_ref, t)
+    assert m["dice"].shape == (B,) and m["iou"].shape == (B,)
+    assert torch.allclose(m["dice"].cpu(), dice_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(m["iou"].cpu(), iou_ref, rtol=1e-5, atol=1e-6)
+    # no-grad (validation) path
+    with torch.no_grad():
+        crit(u.to(dev), t.to(dev))
+    mv = crit.last_batch_metrics()
+    d2, i2 = _ref_dice_iou(u, t)
+    assert torch.allclose(mv["dice"].cpu(), d2, rtol=1e-5, atol=1e-6) and torch.allclose(mv["iou"].cpu(), i2, rtol=1e-5, atol=1e-6)
+    crit.enable_batch_metrics(None)
