@@ -1,0 +1,84 @@
+"""Data-parallel check on REAL GPUs (one process per GPU); run under torchrun:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu_check.py
+
+Every rank holds a shard of one global batch (generated identically on every rank), evaluates the Stage II
+loss through the module API -- first with the NCCL all-reduce of the sums, then with the peer-memory
+exchange (sharding.enable_peer_exchange) -- and compares loss, components and its slice of the gradient
+with (a) the single-shard evaluation of the whole batch on its own GPU and (b) the CPU oracle.
+tests/test_multigpu_spawn.py launches this when at least two GPUs are visible."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    import physics_informed_image_segmentation_b200 as P
+    from physics_informed_image_segmentation_b200 import functional as Fn, sharding
+    from oracle import pil_oracle as po
+    from tests.helpers import blob_inputs, rel_max, rel_scalar
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+
+    B, H, W = 2 * world + 1, 96, 160  # unequal shards on purpose
+    z, t = blob_inputs(B, H, W, seed=5)
+    b0, b1 = sharding.shard_bounds(B, rank, world)
+    kw = dict(dice_weight=0.5, bce_weight=0.5, pde_weight=1e-4, phase_field_weight=1e-4, diffusion_coeff=5.0,
+              reaction_threshold=0.5, epsilon=0.05)
+
+    # (a) whole batch as a single shard on this GPU
+    crit1 = P.DiceBCEPDELoss(**kw).to(dev)
+    x_all = z.to(dev).requires_grad_(True)
+    l_all = crit1.forward_logits(x_all, t.to(dev))
+    l_all.backward()
+    rep_all = crit1.last_report.clone()
+    # (b) oracle
+    comps, og = po.loss_and_grad(z.numpy().astype(np.float64), t.numpy().astype(np.float64), po.STAGE2, po.X_LOGITS_SIGMOID)
+
+    results = {}
+    for mode in ("nccl", "peer"):
+        if mode == "peer":
+            sharding.enable_peer_exchange(dev, None)
+        crit = P.DiceBCEPDELoss(**kw, process_group=dist.group.WORLD, ddp_average=False).to(dev)
+        crit.enable_batch_metrics(0.5)
+        for step in range(3):  # several steps: both mailbox parities, slot reuse
+            x = z[b0:b1].to(dev).requires_grad_(True)
+            loss = crit.forward_logits(x, t[b0:b1].to(dev))
+            loss.backward()
+        torch.cuda.synchronize()
+        rep = crit.last_report
+        for k in range(5):
+            assert rel_scalar(rep[k].item(), rep_all[k].item()) < 2e-6, (mode, k, rep[k].item(), rep_all[k].item())
+            assert rel_scalar(rep[k].item(), comps[k]) < 1e-5, (mode, k)
+        assert rel_max(x.grad.cpu().numpy(), x_all.grad[b0:b1].cpu().numpy()) < 2e-6, mode
+        assert rel_max(x.grad.cpu().numpy(), og[b0:b1]) < 1e-5, mode
+        m = crit.last_batch_metrics()
+        assert m["dice"].shape == (b1 - b0,)
+        # every rank holds the same global report
+        gathered = [torch.empty_like(rep) for _ in range(world)]
+        dist.all_gather(gathered, rep)
+        for g in gathered:
+            assert torch.equal(g[:5], rep[:5]), mode
+        results[mode] = rep[:5].clone()
+    assert torch.equal(results["nccl"], results["peer"]), "peer exchange and all-reduce must agree bit for bit"
+    px = sharding.peer_exchange_for(None, dev)
+    assert px is not None and not px.timed_out()
+    sharding.disable_peer_exchange()
+    dist.barrier()
+    if rank == 0:
+        print(f"multigpu_check ok: world {world}, loss {results['peer'][0].item():.7f} (oracle {comps[0]:.7f})")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
