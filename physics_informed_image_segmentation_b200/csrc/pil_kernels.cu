@@ -1734,10 +1734,6 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
 // ------------------------------------------------------------------------------------------------
 // small kernels: finalize, workspace init, stand-alone PDERegularization operators
 // ------------------------------------------------------------------------------------------------
-__global__ void pil_add_sums_kernel(double* sums, const double* extra) {
-    if (threadIdx.x < PIL_NSUMS && blockIdx.x == 0) sums[threadIdx.x] += extra[threadIdx.x];
-}
-
 __global__ void pil_finalize_kernel(const double* sums, long long n_global, PilParams p, float* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s[PIL_NSUMS];
