@@ -339,7 +339,10 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
-        fwd_med, bwd_med = statistics.median(fwd_ms), statistics.median(bwd_ms)
+        # per-kernel durations in the same regime as `value`: the first K steps of the second pass; the medians
+        # over the whole >= 0.3 s pass (clocks settling under the power cap) are reported beside them
+        fwd_med, bwd_med = statistics.median(fwd_ms[:K]), statistics.median(bwd_ms[:K])
+        fwd_sus, bwd_sus = statistics.median(fwd_ms), statistics.median(bwd_ms)
         bpp_f, bpp_b = 2 * esz, 3 * esz
         ach_b = bpp_b * n_local / (bwd_med * 1e-3) / 1e9
         ach_f = bpp_f * n_local / (fwd_med * 1e-3) / 1e9
@@ -366,10 +369,13 @@ def run_ours(args):
                                   "bwd_rows_per_range": info.bwd_rows_per_segment}},
             "roofline": {"bound": "hbm", "kernel": "pil_bwd_kernel (gradient + stencil sums)", "achieved": ach_b, "peak": peak, "unit": "GB/s",
                          "frac": ach_b / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bpp_b * n_local, "kernel_ms": bwd_med, "kernel_launches_timed": K2,
-                         "note": "kernel_ms: median CUDA-event interval around the launch in a second pass over the same K steps; "
+                         "algorithmic_bytes_per_launch": bpp_b * n_local, "kernel_ms": bwd_med, "kernel_launches_timed": K,
+                         "sustained": {"kernel_ms": bwd_sus, "launches": K2, "frac": bpp_b * n_local / (bwd_sus * 1e-3) / 1e9 / peak},
+                         "note": "kernel_ms: median CUDA-event interval around the launch over the first K steps of a second pass "
+                                 "(an event between the two kernels of every step); sustained: the same over the whole >= 0.3 s pass; "
                                  + ("multi-GPU: the interval includes the wait for the other ranks' sums" if distributed else "single GPU")},
             "roofline_fwd": {"kernel": "pil_point_kernel (pointwise sums)", "achieved": ach_f, "frac": ach_f / peak, "kernel_ms": fwd_med,
+                             "sustained_kernel_ms": fwd_sus,
                              "algorithmic_bytes_per_launch": bpp_f * n_local},
             "roofline_step": {"achieved": ach_step, "frac": ach_step / peak, "bytes_per_pixel": bpp_f + bpp_b},
             "gpu_launches": int(launches), "clocks": clocks, "loss": loss_val, "wall_ms_per_step": 1e3 * wall / K,
