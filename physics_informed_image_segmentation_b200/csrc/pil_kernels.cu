@@ -43,6 +43,29 @@ constexpr float kLogClampLog2 = -100.0f * kLog2e;  // nn.BCELoss clamps ln() at 
 
 static_assert(PIL_NSUMS == 8, "sums layout");
 
+// Development build -DPIL_BOUNDS (tools/bounds_check.py; compute-sanitizer is not available on the GPU
+// pool): every global load / cp.async source / store of the fused kernels is checked against the extents of
+// the tensors of the current call; violations are counted, not trapped.
+#ifdef PIL_BOUNDS
+__device__ const char* g_brd[4] = {nullptr, nullptr, nullptr, nullptr};  // x0, x1, t0, t1 (byte extents)
+__device__ const char* g_bwr[2] = {nullptr, nullptr};                    // grad0, grad1
+__device__ unsigned long long g_berr[4] = {0, 0, 0, 0};                  // bad reads, bad writes, first bad address, -
+__device__ __forceinline__ void chk_rd(const void* p, int bytes) {
+    const char* c = reinterpret_cast<const char*>(p);
+    const bool ok = (c >= g_brd[0] && c + bytes <= g_brd[1]) || (c >= g_brd[2] && c + bytes <= g_brd[3]);
+    if (!ok && atomicAdd(&g_berr[0], 1ull) == 0) g_berr[2] = (unsigned long long)c;
+}
+__device__ __forceinline__ void chk_wr(const void* p, int bytes) {
+    const char* c = reinterpret_cast<const char*>(p);
+    if (!(c >= g_bwr[0] && c + bytes <= g_bwr[1]) && atomicAdd(&g_berr[1], 1ull) == 0) g_berr[2] = (unsigned long long)c;
+}
+#define PIL_CHK_RD(p, n) chk_rd(p, n)
+#define PIL_CHK_WR(p, n) chk_wr(p, n)
+#else
+#define PIL_CHK_RD(p, n)
+#define PIL_CHK_WR(p, n)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
@@ -88,14 +111,17 @@ template <typename T>
 __device__ __forceinline__ float ld1(const T* p);
 template <>
 __device__ __forceinline__ float ld1<float>(const float* p) {
+    PIL_CHK_RD(p, 4);
     return __ldg(p);
 }
 template <>
 __device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16* p) {
+    PIL_CHK_RD(p, 2);
     return __bfloat162float(*p);
 }
 template <>
 __device__ __forceinline__ float ld1<uint8_t>(const uint8_t* p) {
+    PIL_CHK_RD(p, 1);
     return (float)__ldg(p);
 }
 
@@ -103,10 +129,12 @@ template <typename T>
 __device__ __forceinline__ float4 ld4(const T* p);
 template <>
 __device__ __forceinline__ float4 ld4<float>(const float* p) {
+    PIL_CHK_RD(p, 16);
     return __ldg(reinterpret_cast<const float4*>(p));
 }
 template <>
 __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    PIL_CHK_RD(p, 8);
     const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
     float4 r;
     r.x = __uint_as_float(raw.x << 16);
@@ -117,6 +145,7 @@ __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
 }
 template <>
 __device__ __forceinline__ float4 ld4<uint8_t>(const uint8_t* p) {
+    PIL_CHK_RD(p, 4);
     const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(p));
     return make_float4((float)(raw & 0xff), (float)((raw >> 8) & 0xff), (float)((raw >> 16) & 0xff),
                        (float)(raw >> 24));
@@ -126,10 +155,12 @@ template <typename T>
 __device__ __forceinline__ void st4(T* p, float4 v);
 template <>
 __device__ __forceinline__ void st4<float>(float* p, float4 v) {
+    PIL_CHK_WR(p, 16);
     __stcs(reinterpret_cast<float4*>(p), v);
 }
 template <>
 __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+    PIL_CHK_WR(p, 8);
     __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
     uint2 raw;
     raw.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -140,10 +171,12 @@ template <typename T>
 __device__ __forceinline__ void st1(T* p, float v);
 template <>
 __device__ __forceinline__ void st1<float>(float* p, float v) {
+    PIL_CHK_WR(p, 4);
     *p = v;
 }
 template <>
 __device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+    PIL_CHK_WR(p, 2);
     *p = __float2bfloat16_rn(v);
 }
 
@@ -160,6 +193,7 @@ constexpr int kSmemPerBlock = kWarpsPerBlock * kSmemPerWarp;
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async(uint32_t dst_shared, const void* src) {
+    PIL_CHK_RD(src, BYTES);
     if constexpr (BYTES == 16) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
     } else {
@@ -1845,6 +1879,20 @@ __global__ void __launch_bounds__(256) pil_reaction_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static size_t dtype_size(int d);
+#ifdef PIL_BOUNDS
+static void set_bounds(const void* x, const void* t, const void* grad, int64_t n, int x_dtype, int t_dtype) {
+    cudaDeviceSynchronize();  // development build: serialise, the extents are globals
+    const char* rd[4] = {(const char*)x, (const char*)x + n * dtype_size(x_dtype), (const char*)t, (const char*)t + n * dtype_size(t_dtype)};
+    const char* wr[2] = {(const char*)grad, grad ? (const char*)grad + n * dtype_size(x_dtype) : (const char*)grad};
+    cudaMemcpyToSymbol(g_brd, rd, sizeof(rd));
+    cudaMemcpyToSymbol(g_bwr, wr, sizeof(wr));
+}
+#define PIL_SET_BOUNDS(x, t, g, n, xd, td) set_bounds(x, t, g, n, xd, td)
+#else
+#define PIL_SET_BOUNDS(x, t, g, n, xd, td)
+#endif
+
 static int check_common(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
                         int x_kind, const PilParams* p) {
     if (!x || !t || !p) return PIL_ERR_NULL;
@@ -2301,6 +2349,7 @@ static int forward_impl(const void* x, const void* t, int64_t B, int64_t H, int6
     a.sums = sums;
     a.loss_out = loss_out;
     a.p = *p;
+    PIL_SET_BOUNDS(x, t, nullptr, B * H * W, x_dtype, t_dtype);
     const bool aligned = is_aligned_case(x, t, nullptr, W, x_dtype, t_dtype);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t avail = workspace_bytes - wl.partials_off;
@@ -2403,6 +2452,7 @@ static int backward_impl(const void* x, const void* t, void* grad, int64_t B, in
         a.task_counter = a.ticket + 1;
         a.partials = reinterpret_cast<double*>((char*)acc_ws + wl.partials_off);
     }
+    PIL_SET_BOUNDS(x, t, grad, B * H * W, x_dtype, t_dtype);
     const bool aligned = is_aligned_case(x, t, grad, W, x_dtype, t_dtype);
     cudaStream_t s = (cudaStream_t)stream;
     LaunchOut lo;
@@ -2460,6 +2510,7 @@ static int pointwise_impl(const void* x, const void* t, int64_t B, int64_t H, in
     st = make_xchg(ex, &a.X);
     if (st != PIL_OK) return st;
     // flat stream: only total size and base alignment matter
+    PIL_SET_BOUNDS(x, t, nullptr, B * H * W, x_dtype, t_dtype);
     const bool aligned = (a.n % 4 == 0) && is_aligned_case(x, t, nullptr, 4, x_dtype, t_dtype);
     cudaStream_t s = (cudaStream_t)stream;
     int blocks = 0;
@@ -2572,6 +2623,7 @@ int pil_forward_pointwise_metrics(const void* x, const void* t, int64_t B, int64
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(image_counts, 0, (size_t)B * 4 * sizeof(double), s);
     if (e != cudaSuccess) return (int)e;
+    PIL_SET_BOUNDS(x, t, nullptr, B * H * W, x_dtype, t_dtype);
     const bool aligned = (a.hw % 4 == 0) && is_aligned_case(x, t, nullptr, 4, x_dtype, t_dtype);
     int blocks = 0;
     switch (x_kind) {
@@ -2681,6 +2733,16 @@ int pil_last_launch_info(PilLaunchInfo* out) {
     out->kernels_launched = g_kernels_launched;
     return PIL_OK;
 }
+
+#ifdef PIL_BOUNDS
+int pil_debug_bounds(unsigned long long* out4) {  // {bad reads, bad writes, first bad address, 0}; resets the counters
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out4, pil::g_berr, sizeof(unsigned long long) * 4);
+    unsigned long long z[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(pil::g_berr, z, sizeof(z));
+    return (int)e;
+}
+#endif
 
 #ifdef PIL_TIMELINE
 int pil_debug_timeline(void* buf) { return (int)cudaMemcpyToSymbol(pil::g_timeline, &buf, sizeof(buf)); }
