@@ -10,11 +10,13 @@ from .functional import LossParams
 from .sharding import shard_bounds, all_reduce_sums, loss_report_from_sums
 from .session import HostSession
 from .sweep import sweep_losses, s2_grid, s3_grid
+from .metrics import compute_dice_score, compute_dice_score_batch, compute_iou, compute_iou_batch
 from .integration import install_into_reference, use_logits_head
 
 __all__ = [
     "DiceBCELoss", "DiceBCEPDELoss", "PDERegularization", "create_pde_regularization", "LossParams",
     "shard_bounds", "all_reduce_sums", "loss_report_from_sums", "HostSession",
     "install_into_reference", "use_logits_head", "sweep_losses", "s2_grid", "s3_grid",
+    "compute_dice_score", "compute_dice_score_batch", "compute_iou", "compute_iou_batch",
 ]
 __version__ = "0.1.0"

@@ -274,6 +274,28 @@ def backward_accumulate(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: i
     return out, stencil_sums
 
 
+# most recent per-image threshold counts, keyed on the exact tensors they were computed from
+_LAST_COUNTS = None
+
+
+def remember_counts(x: torch.Tensor, t: torch.Tensor, kind: int, threshold: float, counts: torch.Tensor) -> None:
+    import weakref
+
+    global _LAST_COUNTS
+    _LAST_COUNTS = (weakref.ref(x), x._version, weakref.ref(t), t._version, int(kind), float(threshold), counts)
+
+
+def cached_counts(x: torch.Tensor, t: torch.Tensor, kind: int, threshold: float) -> Optional[torch.Tensor]:
+    """The counts of the last fused evaluation if it saw exactly these tensors (same objects, same version
+    counters -- a tensor that merely reuses the address never hits), same input kind and threshold."""
+    if _LAST_COUNTS is None:
+        return None
+    wx, vx, wt, vt, k, thr, counts = _LAST_COUNTS
+    if wx() is x and x._version == vx and wt() is t and t._version == vt and k == int(kind) and thr == float(threshold):
+        return counts
+    return None
+
+
 def forward_pointwise_metrics(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, threshold: float = 0.5,
                               sums: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
                               ex: Optional["_lib.PilExchange"] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -525,11 +547,15 @@ def fused_loss_with_counts(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind
     check_maps(x, t)
     if x.requires_grad and torch.is_grad_enabled():
         loss, report, counts = _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average, metrics_threshold)
-        return loss, report, (counts if metrics_threshold is not None else None)
+        if metrics_threshold is None:
+            return loss, report, None
+        remember_counts(x, t, kind, metrics_threshold, counts)
+        return loss, report, counts
     loss, report = fused_loss(x, t, p, kind, which, group, ddp_average)
     counts = None
     if metrics_threshold is not None:
         _, counts = forward_pointwise_metrics(x.detach(), t.detach(), p, kind, metrics_threshold)
+        remember_counts(x, t, kind, metrics_threshold, counts)
     return loss, report, counts
 
 

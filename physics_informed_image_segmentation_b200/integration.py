@@ -15,7 +15,8 @@ from __future__ import annotations
 import contextlib
 import sys
 
-from .loss import DiceBCELoss, DiceBCEPDELoss
+from . import metrics as _metrics
+from .loss import DiceBCELoss, DiceBCEPDELoss, _FusedLossBase
 from .pde import PDERegularization, create_pde_regularization
 
 _NAMES = {
@@ -24,16 +25,30 @@ _NAMES = {
     "PDERegularization": PDERegularization,
     "create_pde_regularization": create_pde_regularization,
 }
+# the thresholded accuracy metrics train_epoch / validate call on every step (src/train.py:154-155, :257-258)
+_METRIC_NAMES = {
+    "compute_dice_score": _metrics.compute_dice_score,
+    "compute_dice_score_batch": _metrics.compute_dice_score_batch,
+    "compute_iou": _metrics.compute_iou,
+    "compute_iou_batch": _metrics.compute_iou_batch,
+}
 
 
-def install_into_reference(package: str = "src") -> list:
+def install_into_reference(package: str = "src", track_metrics: bool = True) -> list:
     """Rebind the loss/PDE names inside the imported reference package.  Returns the list of
-    (module, name) pairs that were replaced."""
+    (module, name) pairs that were replaced.  With track_metrics (default) the four thresholded Dice/IoU
+    functions are rebound too and every criterion built afterwards leaves per-image threshold counts
+    (threshold 0.5, the value the reference passes), so those per-step metric calls cost no pass over the maps."""
     replaced = []
+    names = dict(_NAMES)
+    if track_metrics:
+        names.update(_METRIC_NAMES)
+        _FusedLossBase.default_batch_metrics_threshold = 0.5
+    _names_backup = names
     for modname, mod in list(sys.modules.items()):
         if mod is None or not (modname == package or modname.startswith(package + ".")):
             continue
-        for name, new in _NAMES.items():
+        for name, new in _names_backup.items():
             if hasattr(mod, name) and getattr(mod, name) is not new:
                 setattr(mod, name, new)
                 replaced.append((modname, name))

@@ -43,6 +43,11 @@ class _FusedBCE(nn.Module):
 
 
 class _FusedLossBase(nn.Module):
+    # Threshold new instances start with (None = off).  integration.install_into_reference(track_metrics=True)
+    # sets it to 0.5 so that criteria built INSIDE the unmodified reference code produce the per-image counts
+    # its per-step compute_dice_score_batch / compute_iou_batch calls are then served from.
+    default_batch_metrics_threshold: Optional[float] = None
+
     def _init_runtime(self, process_group, ddp_average: bool):
         self.process_group = process_group
         self.ddp_average = ddp_average
@@ -50,7 +55,7 @@ class _FusedLossBase(nn.Module):
         self.last_report: Optional[torch.Tensor] = None
         # Per-step accuracy metrics (reference src/train.py:153-160): set to a threshold (0.5 in the
         # reference) to have every forward also leave per-image threshold counts; None = off.
-        self.batch_metrics_threshold: Optional[float] = None
+        self.batch_metrics_threshold: Optional[float] = type(self).default_batch_metrics_threshold
         self._last_counts: Optional[torch.Tensor] = None
 
     def _params(self) -> LossParams:

@@ -149,12 +149,38 @@ def test_install_into_reference_rebinds_names():
     sub.DiceBCELoss = Old
     pkg.PDERegularization = Old
     sys.modules["fakeref"], sys.modules["fakeref.train"] = pkg, sub
+    sub.compute_iou_batch = Old
+    from physics_informed_image_segmentation_b200.loss import _FusedLossBase
     try:
         rep = P.install_into_reference("fakeref")
         assert sub.DiceBCEPDELoss is P.DiceBCEPDELoss and sub.DiceBCELoss is P.DiceBCELoss
-        assert pkg.PDERegularization is P.PDERegularization and len(rep) == 3
+        assert pkg.PDERegularization is P.PDERegularization and len(rep) == 4
+        # the per-step metric calls are rebound too, and criteria built from now on leave the counts they need
+        assert sub.compute_iou_batch is P.compute_iou_batch
+        assert P.DiceBCEPDELoss().batch_metrics_threshold == 0.5
+        _FusedLossBase.default_batch_metrics_threshold = None
+        sub.compute_iou_batch = Old
+        rep = P.install_into_reference("fakeref", track_metrics=False)
+        assert sub.compute_iou_batch is Old and rep == [] and P.DiceBCEPDELoss().batch_metrics_threshold is None
     finally:
+        _FusedLossBase.default_batch_metrics_threshold = None
         del sys.modules["fakeref"], sys.modules["fakeref.train"]
+    # same signatures as the reference's functions (checked live when the checkout is present)
+    import inspect
+    sig = inspect.signature(P.compute_dice_score_batch)
+    assert list(sig.parameters) == ["predictions", "targets", "threshold", "smooth"]
+    assert sig.parameters["threshold"].default == 0.5 and sig.parameters["smooth"].default == 1e-6
+    for f in (P.compute_dice_score, P.compute_iou, P.compute_iou_batch):
+        assert inspect.signature(f) == sig
+    if os.path.exists("/root/reference/src/metrics.py"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_metrics_only", "/root/reference/src/metrics.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        for name in ("compute_dice_score", "compute_dice_score_batch"):
+            rs = inspect.signature(getattr(ref, name))
+            assert list(rs.parameters) == list(sig.parameters)
+            assert all(rs.parameters[k].default == sig.parameters[k].default for k in ("threshold", "smooth"))
 
     class M:
         activation_name = "sigmoid"

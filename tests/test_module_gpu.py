@@ -327,3 +327,42 @@ def test_batch_metrics_ride_on_the_training_step(dev, shape, entry):
     d2, i2 = _ref_dice_iou(u, t)
     assert torch.allclose(mv["dice"].cpu(), d2, rtol=1e-5, atol=1e-6) and torch.allclose(mv["iou"].cpu(), i2, rtol=1e-5, atol=1e-6)
     crit.enable_batch_metrics(None)
+
+
+def test_metric_drop_ins_and_count_cache(dev):
+    """compute_dice_score(_batch) / compute_iou(_batch) with the reference's signatures: values match the
+    reference formulas; after a loss evaluation with batch metrics on the SAME tensors they launch no pass over
+    the maps (only the tiny per-image finalisation)."""
+    import physics_informed_image_segmentation_b200 as P
+    from physics_informed_image_segmentation_b200 import functional as Fn
+    from tests.helpers import blob_inputs
+
+    B, H, W = 5, 80, 112
+    z, t = blob_inputs(B, H, W, seed=41)
+    u = torch.sigmoid(z)
+    ud, td = u.to(dev), t.to(dev)
+    dice_ref, iou_ref = _ref_dice_iou(u, t)
+    assert torch.allclose(P.compute_dice_score_batch(ud, td).cpu(), dice_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(P.compute_iou_batch(ud, td, threshold=0.5).cpu(), iou_ref, rtol=1e-5, atol=1e-6)
+    pb = (u > 0.5).float()
+    I, Pn, T = (pb * t).sum().double(), pb.sum().double(), t.sum().double()
+    assert abs(P.compute_dice_score(ud, td).item() - float((2 * I + 1e-6) / (Pn + T + 1e-6))) < 1e-6
+    assert abs(P.compute_iou(ud, td).item() - float((I + 1e-6) / (Pn + T - I + 1e-6))) < 1e-6
+    d3, _ = _ref_dice_iou(u, t, thr=0.3)
+    assert torch.allclose(P.compute_dice_score_batch(ud, td, threshold=0.3).cpu(), d3, rtol=1e-5, atol=1e-6)
+
+    crit = P.DiceBCEPDELoss(pde_weight=1e-4, phase_field_weight=1e-4, diffusion_coeff=5.0).to(dev).enable_batch_metrics(0.5)
+    x = ud.clone().requires_grad_(True)
+    loss = crit(x, td)
+    k0 = Fn.launch_info().kernels_launched
+    d = P.compute_dice_score_batch(x, td, threshold=0.5)       # what src/train.py:154-155 calls right after the loss
+    i = P.compute_iou_batch(x, td, threshold=0.5)
+    assert Fn.launch_info().kernels_launched - k0 == 2          # two B-element finalisations, no pass over the maps
+    assert torch.allclose(d.cpu(), dice_ref, rtol=1e-5, atol=1e-6) and torch.allclose(i.cpu(), iou_ref, rtol=1e-5, atol=1e-6)
+    loss.backward()
+    # a different threshold, or a modified tensor, is not served from the cache
+    k0 = Fn.launch_info().kernels_launched
+    P.compute_dice_score_batch(x, td, threshold=0.4)
+    assert Fn.launch_info().kernels_launched - k0 == 2          # counts kernel + finalisation
+    with pytest.raises(RuntimeError):
+        P.compute_dice_score_batch(u, t)                          # CPU tensors: no fallback
