@@ -307,7 +307,8 @@ def test_forced_segment_lengths_agree(Fn, po, dev):
 # training-step split: pointwise forward + accumulating backward (pil_loss_fwd_bwd)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,kind", [((8, 256, 256), 1), ((3, 127, 129), 1), ((2, 3, 5), 0), ((1, 2, 2), 1),
-                                        ((5, 17, 36), 0), ((2, 70, 1024), 1), ((1, 33, 240), 2), ((1, 7, 1001), 1)])
+                                        ((5, 17, 36), 0), ((2, 70, 1024), 1), ((1, 33, 240), 2), ((1, 7, 1001), 1),
+                                        ((8, 128, 128), 1), ((4, 100, 99), 0), ((2, 64, 2), 2), ((1, 2, 300), 1)])
 def test_split_step_equals_full_path_and_oracle(Fn, po, dev, shape, kind):
     """pil_loss_fwd_bwd (stencils evaluated once, in the backward kernel) must give the same sums, loss
     report and gradient as pil_forward + pil_backward, and match the oracle."""
