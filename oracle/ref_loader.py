@@ -47,3 +47,20 @@ def loss():
 
 def unet():
     return _load("unet")
+
+
+def metrics():
+    return _load("metrics")
+
+
+def evaluate():
+    """src/evaluate.py (compute_iou, compute_iou_batch): needs scipy + cv2 (present in the build container)
+    and, through its relative imports, src/metrics.py and src/dataset.py."""
+    _load("metrics")
+    try:
+        _load("dataset")
+    except Exception:  # dataset.py may want packages that are absent; evaluate.py only needs the name
+        stub = types.ModuleType(f"{_PKG}.dataset")
+        stub.CellSegmentationDataset = object
+        sys.modules[f"{_PKG}.dataset"] = stub
+    return _load("evaluate")

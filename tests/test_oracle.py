@@ -175,3 +175,53 @@ def test_finalize_gates():
     assert out[0] == pytest.approx(0.5 * dice + 0.5 * 0.4, rel=1e-14)
     p2 = po.Params(pde_weight=2.0, phase_field_weight=3.0)
     assert po.finalize(s, 100, p2)[0] == pytest.approx(0.5 * dice + 0.5 * 0.4 + 2 * 0.03 + 3 * 0.07, rel=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors of the widened path (tests/golden/make_golden_ext.py): S2/S3 grids and Dice/IoU metrics,
+# produced by the real reference
+# ------------------------------------------------------------------------------------------------
+def _ext():
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ext.npz")
+    data = np.load(path)
+    return data, json.loads(bytes(data["meta"]).decode())
+
+
+def test_oracle_matches_reference_on_the_s2_s3_grids():
+    """the C oracle, evaluated once per grid setting, against the reference's DiceBCEPDELoss per setting"""
+    from oracle import pil_oracle as po
+
+    data, meta = _ext()
+    u64, t64 = data["u"].astype(np.float64), data["t"].astype(np.float64)
+    for k, kw in enumerate(meta["grid"]):
+        p = po.Params(dice_weight=0.5, bce_weight=0.5, smooth=1e-6, **kw)
+        s = po.sums(u64, t64, p, po.X_PROB)
+        comps = po.finalize(s, int(s[7]), p)
+        ref = data["sweep_f64"][k]
+        for c in range(5):
+            if c == 4 and not kw["phase_field_weight"] > 0:
+                assert abs(comps[c] - ref[c]) <= 1e-11 * abs(ref[c])  # logged by the reference even when its weight is 0
+                continue
+            assert abs(comps[c] - ref[c]) <= 1e-11 * max(abs(ref[c]), 1e-30), (k, c, comps[c], ref[c])
+        # and the reference's own fp32 evaluation agrees with its fp64 one to fp32 noise
+        assert abs(data["sweep_f32"][k][0] - ref[0]) <= 2e-6 * abs(ref[0])
+
+
+def test_metric_formulas_match_reference_golden():
+    """the three-counts formulation (what pil_image_metrics evaluates) against the reference's functions"""
+    data, _ = _ext()
+    u, t = data["u"], data["t"]
+    for thr, tag in ((0.5, "thr5"), (0.3, "thr3")):
+        pb = (u > thr).astype(np.float64)
+        B = u.shape[0]
+        I = (pb * t).reshape(B, -1).sum(1)
+        P = pb.reshape(B, -1).sum(1)
+        T = t.astype(np.float64).reshape(B, -1).sum(1)
+        s = 1e-6
+        assert np.allclose((2 * I + s) / (P + T + s), data[f"dice_batch_{tag}"], rtol=2e-6, atol=0)
+        assert np.allclose((I + s) / (P + T - I + s), data[f"iou_batch_{tag}"], rtol=2e-6, atol=0)
+        assert abs((2 * I.sum() + s) / (P.sum() + T.sum() + s) - data[f"dice_{tag}"]) < 2e-6
+        assert abs((I.sum() + s) / (P.sum() + T.sum() - I.sum() + s) - data[f"iou_{tag}"]) < 2e-6

@@ -74,3 +74,32 @@ def test_sweep_validates_every_setting(dev):
     z, t = iid_inputs(1, 8, 8)
     with pytest.raises(ValueError, match="diffusion_coeff must be positive"):
         P.sweep_losses(z.to(dev), t.to(dev), [Fn.LossParams(), Fn.LossParams(diffusion_coeff=0.0)], activation="sigmoid")
+
+
+def test_sweep_and_metrics_against_reference_golden(dev):
+    """CUDA path against vectors produced by the REAL reference (tests/golden/make_golden_ext.py): the S2+S3
+    grids as one batched evaluation, and the per-image / global thresholded Dice and IoU."""
+    import json
+    import os
+
+    import physics_informed_image_segmentation_b200 as P
+    from physics_informed_image_segmentation_b200 import functional as Fn
+
+    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ext.npz"))
+    meta = json.loads(bytes(data["meta"]).decode())
+    u, t = torch.from_numpy(data["u"]).to(dev), torch.from_numpy(data["t"]).to(dev)
+    grid = [Fn.LossParams(dice_weight=0.5, bce_weight=0.5, smooth=1e-6, **kw) for kw in meta["grid"]]
+    assert [g.diffusion_coeff for g in P.s2_grid()] == [kw["diffusion_coeff"] for kw in meta["grid"][:6]]
+    assert [g.epsilon for g in P.s3_grid()] == [kw["epsilon"] for kw in meta["grid"][6:]]
+    rep = P.sweep_losses(u, t, grid, activation="none").cpu().numpy().astype(np.float64)
+    ref = data["sweep_f64"]
+    for k, kw in enumerate(meta["grid"]):
+        for c in range(5):
+            if c == 4 and not kw["phase_field_weight"] > 0:
+                continue
+            assert rel_scalar(rep[k, c], ref[k, c]) < 1e-5, (k, c, rep[k, c], ref[k, c])
+    for thr, tag in ((0.5, "thr5"), (0.3, "thr3")):
+        assert np.allclose(P.compute_dice_score_batch(u, t, threshold=thr).cpu().numpy(), data[f"dice_batch_{tag}"], rtol=1e-5, atol=1e-7)
+        assert np.allclose(P.compute_iou_batch(u, t, threshold=thr).cpu().numpy(), data[f"iou_batch_{tag}"], rtol=1e-5, atol=1e-7)
+        assert abs(P.compute_dice_score(u, t, threshold=thr).item() - float(data[f"dice_{tag}"])) < 1e-5
+        assert abs(P.compute_iou(u, t, threshold=thr).item() - float(data[f"iou_{tag}"])) < 1e-5
