@@ -157,7 +157,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -389,14 +389,46 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": npx / statistics.median(times) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample_B}x1x{H}x{W} (of {B}x1x{H}x{W}), median of 3 after 1 warm-up, "
                                               f"torch {torch.__version__} CPU ops, op-for-op port of the reference loss"}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if px is not None:
         px.close()
     if distributed:
         dist.destroy_process_group()
 
 
+class _StdoutGuard:
+    """Everything libraries write to stdout while the benchmark runs (NCCL prints its version banner there)
+    goes to stderr; the ONE JSON line is written to the real stdout at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str) -> None:
+        sys.stdout.flush()
+        os.write(self._real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+
+
+_GUARD = None
+
+
+def emit_line(line: dict) -> None:
+    text = json.dumps(line)
+    if _GUARD is not None:
+        _GUARD.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global _GUARD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -409,10 +441,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with _StdoutGuard() as guard:
+        _GUARD = guard
+        try:
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+        finally:
+            _GUARD = None
 
 
 if __name__ == "__main__":
