@@ -312,6 +312,10 @@ int pil_last_launch_info(PilLaunchInfo* out);
 
 /* Tuning override for benchmarks (0 = automatic): rows per segment for fwd / bwd. */
 int pil_set_tuning(int fwd_rows_per_segment, int bwd_rows_per_segment);
+/* How many MB at the end of each fp32 map the pointwise forward asks L2 to keep (evict_last) for the backward
+ * kernel, which starts there; the rest of its stream is evict_first.  0 = plain loads; negative = default
+ * (PIL_L2_KEEP_MB or 12). */
+int pil_set_l2_keep_mb(int mb);
 
 #ifdef __cplusplus
 }

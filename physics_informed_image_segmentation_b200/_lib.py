@@ -162,6 +162,7 @@ _SIGS = {
     "pil_session_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pil_last_launch_info": (ctypes.c_int, [ctypes.POINTER(PilLaunchInfo)]),
     "pil_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "pil_set_l2_keep_mb": (ctypes.c_int, [ctypes.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -26,6 +26,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "pil.h"
 
 namespace pil {
@@ -996,6 +998,7 @@ constexpr int kPointUnroll = 4;  // float4 pairs in flight per thread
 struct PointArgs {
     const void* x;
     const void* t;
+    long long keep_from4;    // fp32 maps: float4 index from which the loads ask L2 to keep the lines (evict_last)
     long long n;             // pixels in the shard
     double* partials;
     unsigned int* ticket;
@@ -1023,10 +1026,34 @@ __global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const Point
     if constexpr (ALIGNED) {
         const long long n4 = A.n >> 2;  // n % 4 == 0 on this path
         long long i = tid;
+        // L2 policy (fp32 maps).  The backward kernel walks the shard from its END, so the last few MB of x and t
+        // this front-to-back stream reads are what it needs first: those loads carry an evict_last hint.  All
+        // the others are evict_first: a 537 MB stream has no business displacing the gradient lines the
+        // previous backward left dirty in L2 (their write-back then interleaves with these reads).
+        unsigned long long pol_keep = 0, pol_stream = 0;
+        constexpr bool kHint = std::is_same<XT, float>::value && std::is_same<TT, float>::value;
+        if constexpr (kHint) {
+            asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+        }
+        auto ldh = [&](const float* p, unsigned long long pol) -> float4 {
+            float4 r;
+            asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+            return r;
+        };
         for (; i + (kPointUnroll - 1) * stride < n4; i += kPointUnroll * stride) {
             float4 xv[kPointUnroll], tv[kPointUnroll];
 #pragma unroll
             for (int q = 0; q < kPointUnroll; ++q) {
+                if constexpr (kHint) {
+                    if (A.keep_from4 < n4) {
+                        const unsigned long long pol = (i + q * stride >= A.keep_from4) ? pol_keep : pol_stream;
+                        xv[q] = ldh(reinterpret_cast<const float*>(x) + 4 * (i + q * stride), pol);
+                        tv[q] = ldh(reinterpret_cast<const float*>(t) + 4 * (i + q * stride), pol);
+                        continue;
+                    }
+                }
                 xv[q] = ld4<XT>(x + 4 * (i + q * stride));
                 tv[q] = ld4<TT>(t + 4 * (i + q * stride));
             }
@@ -1918,6 +1945,7 @@ static bool is_aligned_case(const void* x, const void* t, const void* gptr, int6
 static thread_local PilLaunchInfo t_info = {};
 static long long g_kernels_launched = 0;
 static int g_tune_fwd_rps = 0, g_tune_bwd_rps = 0;
+static long long g_l2_keep_mb = -1;  // pil_set_l2_keep_mb; < 0: PIL_L2_KEEP_MB or the default
 
 static int sm_count() {
     static int n = 0;
@@ -2503,6 +2531,19 @@ static int pointwise_impl(const void* x, const void* t, int64_t B, int64_t H, in
     a.x = x;
     a.t = t;
     a.n = (long long)B * H * W;
+    {
+        long long keep_mb = g_l2_keep_mb;
+        if (keep_mb < 0) {
+            static long long env_mb = -2;
+            if (env_mb == -2) {
+                const char* e = getenv("PIL_L2_KEEP_MB");
+                env_mb = e ? atoll(e) : 12;  // interleaved A/B at 64x1024^2: 8-16 MB per map 2-3% faster per step than 0, 40 no better
+            }
+            keep_mb = env_mb;
+        }
+        const long long keep4 = (keep_mb << 20) / 16;  // float4s of EACH map to keep
+        a.keep_from4 = (keep_mb > 0 && (a.n >> 2) > 2 * keep4) ? (a.n >> 2) - keep4 : (a.n >> 2);
+    }
     a.ticket = reinterpret_cast<unsigned int*>((char*)workspace + wl.ticket_off);
     a.partials = reinterpret_cast<double*>((char*)workspace + wl.partials_off);
     a.sums = sums;
@@ -2747,6 +2788,11 @@ int pil_debug_bounds(unsigned long long* out4) {  // {bad reads, bad writes, fir
 #ifdef PIL_TIMELINE
 int pil_debug_timeline(void* buf) { return (int)cudaMemcpyToSymbol(pil::g_timeline, &buf, sizeof(buf)); }
 #endif
+
+int pil_set_l2_keep_mb(int mb) {
+    g_l2_keep_mb = mb;
+    return PIL_OK;
+}
 
 int pil_set_tuning(int fwd_rows_per_segment, int bwd_rows_per_segment) {
     g_tune_fwd_rps = fwd_rows_per_segment > 0 ? fwd_rows_per_segment : 0;

@@ -22,6 +22,7 @@ ap.add_argument("--rps-bwd", type=int, default=0)
 ap.add_argument("--kind", type=int, default=1)
 ap.add_argument("--shape", default="")
 ap.add_argument("--mode", default="split", choices=["split", "full", "fused"])
+ap.add_argument("--rotate", type=int, default=1, help="fused mode: cycle through this many gradient buffers (no L2 carry-over of dirty lines)")
 a = ap.parse_args()
 B, H, W, name = bench.WORKLOADS[a.workload]
 if a.shape:
@@ -61,9 +62,10 @@ if a.mode == "fused":
     for _ in range(3):
         Fn.loss_fwd_bwd(z, t, p, a.kind, grad=g, sums=sums, report=rep)
     torch.cuda.synchronize()
+    gs = [g] + [torch.empty_like(g) for _ in range(a.rotate - 1)]
     e0.record()
-    for _ in range(a.steps):
-        Fn.loss_fwd_bwd(z, t, p, a.kind, grad=g, sums=sums, report=rep)
+    for k in range(a.steps):
+        Fn.loss_fwd_bwd(z, t, p, a.kind, grad=gs[k % a.rotate], sums=sums, report=rep)
     e1.record()
     torch.cuda.synchronize()
     per = e0.elapsed_time(e1) / a.steps
