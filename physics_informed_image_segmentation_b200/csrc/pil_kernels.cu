@@ -1139,6 +1139,7 @@ struct PointMetricsArgs {
     PilParams p;
     double* image_counts;  // [B][4], zero on entry
     float threshold;
+    int l2_stream;         // fp32 maps: loads carry an L2 evict_first hint (see pil_point_kernel)
     XchgDev X;
 };
 
@@ -1169,11 +1170,27 @@ __global__ void __launch_bounds__(kPointThreads, 3) pil_point_metrics_kernel(con
         if constexpr (ALIGNED) {
             long long i = lo + threadIdx.x;
             constexpr long long S = kPointThreads;
+            constexpr bool kHint = std::is_same<XT, float>::value && std::is_same<TT, float>::value;
+            unsigned long long pol_stream = 0;
+            if constexpr (kHint) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+            auto ldh = [&](const float* p) -> float4 {
+                float4 r;
+                asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                             : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol_stream));
+                return r;
+            };
             for (; i < hi; i += kPointUnroll * S) {
                 float4 xv[kPointUnroll], tv[kPointUnroll];
 #pragma unroll
                 for (int q = 0; q < kPointUnroll; ++q) {
                     if (i + q * S < hi) {
+                        if constexpr (kHint) {
+                            if (A.l2_stream) {
+                                xv[q] = ldh(reinterpret_cast<const float*>(x) + 4 * (i + q * S));
+                                tv[q] = ldh(reinterpret_cast<const float*>(t) + 4 * (i + q * S));
+                                continue;
+                            }
+                        }
                         xv[q] = ld4<XT>(x + 4 * (i + q * S));
                         tv[q] = ld4<TT>(t + 4 * (i + q * S));
                     }
@@ -2659,6 +2676,7 @@ int pil_forward_pointwise_metrics(const void* x, const void* t, int64_t B, int64
     a.p = *p;
     a.image_counts = image_counts;
     a.threshold = threshold;
+    a.l2_stream = g_l2_keep_mb != 0 ? 1 : 0;
     st = make_xchg(ex, &a.X);
     if (st != PIL_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
