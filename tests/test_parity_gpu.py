@@ -436,3 +436,28 @@ def test_full_size_dynamic_step_matches_static_kernels(Fn, po, dev):
     og = po.backward(z[sl].cpu().numpy().astype(np.float64), t[sl].cpu().numpy().astype(np.float64), po.STAGE2,
                      sums.cpu().numpy(), z.numel(), 1)
     assert rel_max(grad[sl].cpu().numpy(), og) < TOL
+
+
+def test_l2_cache_hints_do_not_change_results(Fn, po, dev):
+    """The pointwise forward's L2 eviction hints (evict_first stream, evict_last tail; pil_set_l2_keep_mb) are a
+    pure performance knob: sums, loss report and gradient are bit-identical with and without them, also when
+    the kept tail covers part / nothing / almost all of the maps."""
+    from physics_informed_image_segmentation_b200 import _lib
+
+    z, t = blob_inputs(6, 256, 512, seed=12)   # 3 MB per map
+    x, tt, p = z.to(dev), t.to(dev), lp(Fn, po.STAGE2)
+    base = None
+    try:
+        for mb in (0, 1, 2, 64, -1):
+            _lib.lib().pil_set_l2_keep_mb(mb)
+            s = Fn.forward_pointwise(x, tt, p, 1).clone()
+            rep, sums, g = Fn.loss_fwd_bwd(x, tt, p, 1)
+            _, counts = Fn.forward_pointwise_metrics(x, tt, p, 1, 0.5)
+            cur = (s, rep.clone(), sums.clone(), g.clone(), counts.clone())
+            if base is None:
+                base = cur
+            else:
+                for a, b in zip(cur, base):
+                    assert torch.equal(a, b), f"keep {mb} MB changed a result"
+    finally:
+        _lib.lib().pil_set_l2_keep_mb(-1)
