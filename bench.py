@@ -138,13 +138,22 @@ def cpu_port_time(sample_B, H, W, iters, warm):
 
 
 def run_reference(args):
-    """--impl reference: rank 0 only; each step = a bounded sample (4 images) of the workload."""
+    """--impl reference: rank 0 only.  Each step = a bounded sample of the workload -- up to 4 whole images,
+    fewer (down to a band of rows of one image) when --steps is large -- sized from one probe step so that
+    the whole run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     B, H, W, name = WORKLOADS[args.workload]
-    sample_B = max(1, min(B, (4 * 1024 * 1024) // (H * W)))
-    px, times, cores = cpu_port_time(sample_B, H, W, args.steps, args.warmup)
+    _, probe, _ = cpu_port_time(1, H, W, 1, 1)            # one image, after one warm-up
+    budget_s = 150.0 / max(args.steps + args.warmup, 1)    # per step
+    sample_H = H
+    if probe[0] <= budget_s:
+        sample_B = max(1, min(B, 4, int(budget_s / probe[0])))
+    else:
+        sample_B = 1
+        sample_H = max(16, min(H, int(H * budget_s / probe[0]) // 16 * 16))
+    px, times, cores = cpu_port_time(sample_B, sample_H, W, args.steps, args.warmup)
     total = sum(times)
     value = px * len(times) / total / 1e9
     line = {
@@ -153,7 +162,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}_fp32", "stage2_params": STAGE2, "entry": "sigmoid -> loss -> backward on CPU"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample_B}x1x{H}x{W} per step (of {B}x1x{H}x{W}), torch CPU ops, op-for-op port of the reference"},
+                         "sample": f"{sample_B}x1x{sample_H}x{W} per step (of {B}x1x{H}x{W}), torch CPU ops, op-for-op port of the reference"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
