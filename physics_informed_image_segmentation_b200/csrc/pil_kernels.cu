@@ -38,7 +38,8 @@ constexpr int kStripCols = kOutLanes * kVec;  // 120 output columns per warp
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kFwdMinBlocks = 7;  // 28 warps / SM, <= 73 registers
-constexpr int kBwdMinBlocks = 4;  // 16 warps / SM, <= 128 registers (spilling at 5 blocks costs more than the occupancy gains)
+constexpr int kBwdMinBlocks = 4;  // 16 warps / SM, <= 128 registers.  Measured at 64x1024^2: 145 us; 3 blocks (158 registers,
+                                  // 675-instruction loop) 155 us; 5 blocks (96 registers, spills, 747-instruction loop) 180 us
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kLogClampLog2 = -100.0f * kLog2e;  // nn.BCELoss clamps ln() at -100
