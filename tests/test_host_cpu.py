@@ -253,3 +253,18 @@ def test_sweep_closed_form_matches_direct_evaluation():
                   - 2 * a * (h * g).sum() + a * a * (g * g).sum())
         s = po.sums(u, t, po.Params(diffusion_coeff=D, reaction_threshold=a), po.X_PROB)
         assert abs(closed - s[4]) / s[4] < 1e-12
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/pil.h compiles as C99 (no C++-isms) together with a translation unit that takes the entry points by
+    their documented signatures -- what a cgo / JNI / ctypes binding of the boundary relies on."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    out = tmp_path / "abi_check.o"
+    res = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c",
+                          os.path.join(ROOT, "tests", "abi_check.c"), "-o", str(out)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
