@@ -461,3 +461,43 @@ def test_l2_cache_hints_do_not_change_results(Fn, po, dev):
                     assert torch.equal(a, b), f"keep {mb} MB changed a result"
     finally:
         _lib.lib().pil_set_l2_keep_mb(-1)
+
+
+def test_storage_dtypes_on_the_training_split_and_auxiliary_kernels(Fn, po, dev):
+    """bf16 maps / u8 masks through the kernels the first dtype tests do not reach: the training-step split
+    (pointwise forward + accumulating, dynamically scheduled backward), the moments forward (sweep) and the
+    metrics forward.  Arithmetic is fp32 inside: u8 masks are bit-identical to fp32 masks; bf16 maps agree with
+    the fp32 evaluation of the same up-cast values to the gradient's bf16 store rounding."""
+    from physics_informed_image_segmentation_b200 import _lib
+
+    z, t = blob_inputs(3, 96, 136, seed=8)
+    p = lp(Fn, po.STAGE2)
+    zb = z.bfloat16()
+    x32, t32 = zb.float().to(dev), t.to(dev)             # fp32 storage of the SAME values
+    xb, tb, tu = zb.to(dev), t.bfloat16().to(dev), t.to(torch.uint8).to(dev)
+    grid = [p, Fn.LossParams(pde_weight=1e-3, diffusion_coeff=100.0), Fn.LossParams(pde_weight=1e-4, phase_field_weight=1e-4, epsilon=0.2)]
+    try:
+        _lib.lib().pil_set_tuning(0, 16)                   # short dynamically claimed ranges on a small shape
+        rep_f, sums_f, g_f = Fn.loss_fwd_bwd(x32, t32, p, 1)
+        rep_u, sums_u, g_u = Fn.loss_fwd_bwd(x32, tu, p, 1)
+        rep_b, sums_b, g_b = Fn.loss_fwd_bwd(xb, tb, p, 1)
+        rep_bu, _, g_bu = Fn.loss_fwd_bwd(xb, tu, p, 1)
+    finally:
+        _lib.lib().pil_set_tuning(0, 0)
+    assert torch.equal(rep_f, rep_u) and torch.equal(g_f, g_u) and torch.equal(sums_f, sums_u)
+    assert torch.equal(rep_b, rep_bu) and torch.equal(g_b, g_bu)
+    for k in range(5):
+        assert rel_scalar(rep_b[k].item(), rep_f[k].item()) < 2e-6   # same fp32 arithmetic on the same values
+    assert g_b.dtype == torch.bfloat16
+    assert rel_max(g_b.float().cpu().numpy(), g_f.cpu().numpy()) < 1e-2
+    comps, og = po.loss_and_grad(zb.float().numpy().astype(np.float64), t.numpy().astype(np.float64), po.STAGE2, 1)
+    assert rel_scalar(rep_b[0].item(), comps[0]) < 1e-5 and rel_max(g_b.float().cpu().numpy(), og) < 1e-2
+    # moments forward (sweep) and metrics forward
+    s_f = Fn.sweep_losses(x32, t32, grid, 1)
+    for xs, ts in ((x32, tu), (xb, tb), (xb, tu)):
+        s_o = Fn.sweep_losses(xs, ts, grid, 1)
+        assert torch.allclose(s_o[:, :5], s_f[:, :5], rtol=2e-6, atol=0)
+    _, c_f = Fn.forward_pointwise_metrics(x32, t32, p, 1, 0.5)
+    for xs, ts in ((x32, tu), (xb, tb), (xb, tu)):
+        _, c_o = Fn.forward_pointwise_metrics(xs, ts, p, 1, 0.5)
+        assert torch.equal(c_o, c_f)
