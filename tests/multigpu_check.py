@@ -71,6 +71,17 @@ def main():
             assert torch.equal(g[:5], rep[:5]), mode
         results[mode] = rep[:5].clone()
     assert torch.equal(results["nccl"], results["peer"]), "peer exchange and all-reduce must agree bit for bit"
+    # parameter sweep over the sharded batch (BASELINE config 4): moments all-reduced, K losses of the GLOBAL batch
+    grid = P.s2_grid() + P.s3_grid()
+    sw = P.sweep_losses(z[b0:b1].to(dev), t[b0:b1].to(dev), grid, activation="sigmoid", process_group=dist.group.WORLD)
+    sw_all = P.sweep_losses(z.to(dev), t.to(dev), grid, activation="sigmoid")
+    assert torch.allclose(sw[:, :5], sw_all[:, :5], rtol=2e-6, atol=0)
+    for k, gp in enumerate(grid):
+        pp = po.Params(dice_weight=gp.dice_weight, bce_weight=gp.bce_weight, pde_weight=gp.pde_weight,
+                       phase_field_weight=gp.phase_field_weight, diffusion_coeff=gp.diffusion_coeff,
+                       reaction_threshold=gp.reaction_threshold, epsilon=gp.epsilon, smooth=gp.smooth)
+        s = po.sums(z.numpy().astype(np.float64), t.numpy().astype(np.float64), pp, po.X_LOGITS_SIGMOID)
+        assert rel_scalar(sw[k, 0].item(), po.finalize(s, int(s[7]), pp)[0]) < 1e-5, k
     px = sharding.peer_exchange_for(None, dev)
     assert px is not None and not px.timed_out()
     sharding.disable_peer_exchange()
