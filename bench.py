@@ -408,6 +408,32 @@ def run_ours(args):
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if world == 1 and not args.no_cpu and args.dtype == "f32":
+            # the reference's op sequence (eager PyTorch: reflect pad, 3 one-channel conv2d, BCELoss, ~40 kernels forward,
+            # ~100 backward) on THIS GPU -- what the unmodified reference costs once its tensors are on the B200
+            try:
+                from oracle import pil_oracle as po_
+                from oracle import torch_port
+
+                sb_ = max(1, min(B, (16 * 1024 * 1024) // (H * W)))
+                ze, te = z[:sb_].float().clone(), t[:sb_].float().clone()
+                for _ in range(3):
+                    torch_port.fwd_bwd(ze, te, po_.STAGE2, 1)
+                torch.cuda.synchronize()
+                ee = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ee[0].record()
+                for _ in range(5):
+                    torch_port.fwd_bwd(ze, te, po_.STAGE2, 1)
+                ee[1].record()
+                torch.cuda.synchronize()
+                ms_e = ee[0].elapsed_time(ee[1]) / 5
+                line["gpu_eager_baseline"] = {"value": sb_ * H * W / (ms_e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e,
+                                              "sample": f"{sb_}x1x{H}x{W}, mean of 5 after 3 warm-ups",
+                                              "kind": f"op-for-op port of the reference loss, eager torch {torch.__version__} on the same GPU"}
+                del ze, te
+                torch.cuda.empty_cache()
+            except Exception as exc:  # informational leg: never fail the bench on it
+                line["gpu_eager_baseline"] = {"unavailable": str(exc)[:200]}
         if world == 1 and not args.no_cpu:
             sample_B = max(1, min(B, (8 * 1024 * 1024) // (H * W)))
             npx, times, cores = cpu_port_time(sample_B, H, W, iters=3, warm=1)
