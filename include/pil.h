@@ -121,7 +121,8 @@ int pil_forward(const void* x, const void* t, int64_t B, int64_t H, int64_t W,
  * Assemble the scalar loss from (all-reduced) sums on the device: src/loss.py:134-160.
  * n_global <= 0 means "use sums[7]".
  * loss_out (device, PIL_NOUT floats): [0] total  [1] dice_loss  [2] bce  [3] L_rd  [4] L_pf
- * [5] n_invalid  [6],[7] reserved.  [1..4] are the four quantities train_epoch re-computes for
+ * [5] n_invalid  [6],[7] reserved.  If n_invalid > 0 (probabilities outside [0,1] or NaN, on which the
+ * reference's nn.BCELoss raises) the total is NaN: stream-ordered code cannot raise, it fails loudly instead.  [1..4] are the four quantities train_epoch re-computes for
  * logging at src/train.py:120-150, served here without a second pass over the maps.
  */
 int pil_finalize(const double* sums, int64_t n_global, const PilParams* p, float* loss_out, void* stream);

@@ -406,6 +406,10 @@ __device__ __forceinline__ void finalize_device(const double* s, double n, const
     double total = p.dice_weight * dice_loss + p.bce_weight * bce;
     if (p.pde_weight > 0.0) total += p.pde_weight * rd;
     if (p.phase_field_weight > 0.0) total += p.phase_field_weight * pf;
+    // nn.BCELoss refuses inputs outside [0,1] (the reference's step dies there, src/loss.py:141).  Stream-ordered
+    // code cannot raise, so the total is poisoned instead: a NaN loss is the loudest failure that needs no host
+    // sync.  The count stays in slot 5; the Python module can raise on it (strict_inputs).
+    if (s[6] > 0.0) total = __longlong_as_double(0x7ff8000000000000LL);
     out[0] = (float)total;
     out[1] = (float)dice_loss;
     out[2] = (float)bce;

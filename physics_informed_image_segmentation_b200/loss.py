@@ -56,6 +56,10 @@ class _FusedLossBase(nn.Module):
         # Per-step accuracy metrics (reference src/train.py:153-160): set to a threshold (0.5 in the
         # reference) to have every forward also leave per-image threshold counts; None = off.
         self.batch_metrics_threshold: Optional[float] = type(self).default_batch_metrics_threshold
+        # Probabilities outside [0,1] (or NaN): the reference's nn.BCELoss raises.  The kernels count them and
+        # return a NaN loss without a host sync; with strict_inputs=True the module also raises the reference's
+        # RuntimeError, at the price of one sync per call (the reference's loop syncs anyway at loss.item()).
+        self.strict_inputs: bool = False
         self._last_counts: Optional[torch.Tensor] = None
 
     def _params(self) -> LossParams:
@@ -67,6 +71,8 @@ class _FusedLossBase(nn.Module):
                                                          self.batch_metrics_threshold)
         self.last_report = report
         self._last_counts = counts
+        if self.strict_inputs and kind == Fn.X_PROB and report[Fn.OUT_INVALID].item() > 0:
+            raise RuntimeError("all elements of input should be between 0 and 1")  # nn.BCELoss's message
         # identity (weak) + version counter: a different tensor that merely reuses the address never hits
         self._last = (weakref.ref(x), x._version, weakref.ref(t), t._version, kind, p, report)
         return loss

@@ -162,5 +162,7 @@ def loss_report_from_sums(sums: Sequence[float], n_global: Optional[int], p: Los
         total += p.pde_weight * rd
     if p.phase_field_weight > 0:
         total += p.phase_field_weight * pf
+    if s[6] > 0:  # probabilities outside [0,1]: the reference's nn.BCELoss raises; the device finalize returns NaN
+        total = float("nan")
     return {"loss": total, "dice_loss": dice_loss, "bce_loss": bce, "pde_loss": rd, "phase_field_loss": pf,
             "n_invalid": s[6], "n_pixels": n}

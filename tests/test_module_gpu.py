@@ -188,8 +188,15 @@ def test_input_contract_errors(P, dev):
     bad[0, 0, 0, 0] = 1.5
     bad[1, 0, 3, 3] = float("nan")
     with torch.no_grad():
-        crit(bad, m)
+        loss_bad = crit(bad, m)
     assert crit.last_report[5].item() == 2.0
+    assert torch.isnan(loss_bad)          # no host sync, but not silent either
+    with torch.no_grad():
+        assert torch.isfinite(crit(u, m))
+    crit.strict_inputs = True             # opt-in: the reference's exception (one sync per call)
+    with pytest.raises(RuntimeError, match="between 0 and 1"):
+        crit(bad, m)
+    crit(u, m)
 
 
 def test_pde_operators_and_their_autograd(P, po, dev):
