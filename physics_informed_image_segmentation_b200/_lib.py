@@ -14,12 +14,31 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SO_PATH = os.path.join(CSRC, "libpil.so")
-SOURCES = [os.path.join(CSRC, "pil_kernels.cu"), os.path.join(CSRC, "pil_session.cu")]
-HEADERS = [os.path.join(INCLUDE, "pil.h")]
+OBJ_DIR = os.path.join(CSRC, "obj")
+HEADERS = [os.path.join(INCLUDE, "pil.h"), os.path.join(CSRC, "pil_common.cuh"), os.path.join(CSRC, "pil_fwdrow.cuh")]
+
+# Translation units of libpil.so: (source, extra defines, object name).  The fused kernels are compiled once per
+# input kind (-DPIL_KIND) so that their template instantiations build in parallel.
+_KIND_SOURCES = ("pil_fwd.cu", "pil_point.cu", "pil_bwd.cu")
+_PLAIN_SOURCES = ("pil_api.cu", "pil_session.cu", "pil_tail.cu", "pil_boundary.cu")
+
+
+def _units():
+    units = []
+    for src in _KIND_SOURCES:
+        for k in (0, 1, 2):
+            units.append((os.path.join(CSRC, src), [f"-DPIL_KIND={k}"], f"{src[:-3]}_k{k}.o"))
+    for src in _PLAIN_SOURCES:
+        if os.path.exists(os.path.join(CSRC, src)):
+            units.append((os.path.join(CSRC, src), [], f"{src[:-3]}.o"))
+    return units
+
+
+SOURCES = sorted({u[0] for u in _units()})
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 PIL_NSUMS = 8
@@ -68,23 +87,45 @@ def _stale() -> bool:
     return any(os.path.exists(s) and os.path.getmtime(s) > t for s in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into csrc/libpil.so (in-tree, so it travels with the repo)."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), so_path: str = None) -> str:
+    """Compile csrc/*.cu for sm_100a (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo) into csrc/libpil.so
+    (in-tree, so it travels with the repo).  Objects are compiled in parallel, one nvcc process per unit;
+    only units older than their source or any header are recompiled."""
+    so_path = so_path or SO_PATH
+    if not force and so_path == SO_PATH and not _stale():
         return SO_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("libpil.so is missing/stale and nvcc was not found; this package has no CPU fallback")
-    srcs = [s for s in SOURCES if os.path.exists(s)]
-    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-o", SO_PATH, *srcs]
+    from concurrent.futures import ThreadPoolExecutor
+
+    obj_dir = OBJ_DIR if so_path == SO_PATH and not extra_flags else so_path + ".obj"
+    os.makedirs(obj_dir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in HEADERS if os.path.exists(h))
+
+    def compile_unit(unit):
+        src, defs, obj = unit
+        obj = os.path.join(obj_dir, obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, ""
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, *defs, "-I", INCLUDE, "-I", CSRC, "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {os.path.basename(src)} {' '.join(defs)}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=max(1, min(os.cpu_count() or 1, 12))) as pool:
+        results = list(pool.map(compile_unit, _units()))
+    objs = [r[0] for r in results]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        print("".join(r[1] for r in results))
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so_path, *objs],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
-    return SO_PATH
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    return so_path
 
 
 _lib = None

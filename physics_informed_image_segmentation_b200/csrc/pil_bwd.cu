@@ -1,0 +1,639 @@
+// pil_bwd.cu -- K2, the fused backward kernel (+ stencil sums in accumulate mode), and its launcher.
+// Compiled once per input kind (-DPIL_KIND=0|1|2); without PIL_KIND all three kinds are instantiated here.
+#include "pil_common.cuh"
+
+namespace pil {
+// ------------------------------------------------------------------------------------------------
+// K2: fused backward
+// ------------------------------------------------------------------------------------------------
+struct BwdCoef {
+    float alpha, beta;   // dice: d/du = alpha*t + beta                    (du space)
+    float cb;            // bce : cb*(u-t)/max(uv,1e-12)                   (du space)
+    float cA;            // rd  : cA * (L^T r)      cA = scale*lrd*2/N*D
+    float f3, f2, f1;    // rd  : cF * f'(u) = f3 u^2 + f2 u + f1,  cF = scale*lrd*2/N, f' = -3u^2 + 2(1+a)u - a
+    float cG;            // pf  : cG * (dx[p-1]-dx[p+1] + dy[i-1]-dy[i+1]),  cG = scale*lpf/N*eps/4
+    float cW;            // pf  : cW * uv*(1-2u),   cW = scale*lpf/N*2/eps
+    float D;
+    float a1, c0;        // r = u*(u*(a1 - u) + c0) + D*(sum of 4 neighbours),  a1 = 1+a, c0 = -a - 4D
+    // packed path only
+    float beta_half;     // beta / 2 (travels with the horizontal transposed-stencil terms)
+    float f1c;           // f1 - 4 cA  (centre tap of the transposed Laplacian folded into f')
+    float cW2n;          // -2 cW       (cW uv (1-2u) = uv (cW2n u + cW))
+};
+
+// accumulate mode: reduce the stencil sums across the grid; the last block publishes them and,
+// if asked, assembles the loss from (global pointwise sums + these) -- src/loss.py:144-160.
+static __device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const double* acc, const double* gs) {
+    double raw[PIL_NSUMS];
+    if (!reduce_to_last_block<kThreads, double>(acc, A.partials, A.ticket, raw)) return;
+    __shared__ double s_push[PIL_NSUMS];   // this shard's stencil sums
+    __shared__ double s_glob[PIL_NSUMS];   // the global stencil sums
+    if (threadIdx.x == 0) {
+        double sb[PIL_NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        sb[4] = raw[4];
+        sb[5] = (A.p.epsilon / 8.0) * raw[5];
+#pragma unroll
+        for (int k = 0; k < PIL_NSUMS; ++k) {
+            A.stencil_sums[k] = sb[k];
+            s_push[k] = sb[k];
+            s_glob[k] = sb[k];
+        }
+    }
+    bool finalize = true;
+    if (A.X.world > 0) {  // data parallel: swap the stencil sums with every rank, then finalise globally
+        __syncthreads();
+        xchg_push(A.X, 1, s_push);
+        if (A.X.defer) {
+            finalize = false;
+        } else {
+            xchg_wait_sum(A.X, 1, s_glob);
+        }
+    }
+    if (threadIdx.x == 0) {
+        if ((A.loss_out != nullptr || A.total_sums != nullptr) && finalize) {
+            double tot[PIL_NSUMS];
+#pragma unroll
+            for (int k = 0; k < PIL_NSUMS; ++k) tot[k] = gs[k] + s_glob[k];
+            if (A.loss_out != nullptr) finalize_device(tot, A.n_global > 0 ? (double)A.n_global : tot[7], A.p, A.loss_out);
+            if (A.total_sums != nullptr) {  // every block has read gsums long before the last one gets here
+#pragma unroll
+                for (int k = 0; k < PIL_NSUMS; ++k) A.total_sums[k] = tot[k];
+            }
+        }
+        if (A.task_counter != nullptr) *A.task_counter = 0u;  // every warp has made its last claim
+        *A.ticket = 0u;
+    }
+}
+
+template <int KIND, typename XT, typename TT, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const BwdArgs A) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Geo& g = A.g;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    TL_STAMP(1, 0);
+
+    // task id -> (strip, first row, end row): equal row ranges (+-1 row), `strips` tasks per range
+    // Tasks are handed out from the END of the shard backwards: the pointwise forward is a front-to-back
+    // stream, so the last ~100 MB of x and t it read are still in the 126 MB L2 when this kernel starts.
+    auto decode = [&](long long tk, int& strip_o, long long& pos_o, long long& end_o) {
+        if (A.reverse) tk = g.tasks - 1 - tk;
+        strip_o = (int)(tk % g.strips);
+        const long long grp = tk / g.strips;
+        pos_o = (g.total_rows * grp) / g.groups;
+        end_o = (g.total_rows * (grp + 1)) / g.groups;
+    };
+    // pull the rows a range starts with (2 halo rows + the pipeline depth) into L2; no architectural effect
+    auto prefetch_rows = [&](int strip_p, long long pos_p) {
+        if ((lane & 7) == 0 || lane == 31) {
+            const int colp = min(max(strip_p * kStripCols + (lane - 1) * kVec, 0), g.W - 1);
+            const char* xp = reinterpret_cast<const char*>(A.x) + (pos_p * g.W + colp) * (long long)sizeof(XT);
+            const char* tp = reinterpret_cast<const char*>(A.t) + (pos_p * g.W + colp) * (long long)sizeof(TT);
+#pragma unroll
+            for (int q = -2; q < kStages; ++q) {
+                if (pos_p + q >= 0 && pos_p + q < g.total_rows) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + (long long)q * g.W * (long long)sizeof(XT)));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + (long long)q * g.W * (long long)sizeof(TT)));
+                }
+            }
+        }
+    };
+
+    // ---- PDL prologue: nothing an earlier kernel wrote may be READ before pdl_wait(), but the rows this
+    // warp starts with can already be pulled into L2 (a prefetch has no architectural effect), so the
+    // DRAM latency of the pipeline fill overlaps the tail of the previous kernel.
+    if (task < g.tasks) {
+        int strip_p;
+        long long pos_p, end_p;
+        decode(task, strip_p, pos_p, end_p);
+        prefetch_rows(strip_p, pos_p);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    TL_STAMP(1, 1);
+
+    // ---- global sums: given, or (data parallel) collected from the peer mailbox -----------------
+    __shared__ double s_gs[PIL_NSUMS];
+    const double* gs = A.gsums;
+    if (A.X.world > 0) {
+        xchg_wait_sum(A.X, 0, s_gs);
+        gs = s_gs;
+    }
+
+    if (task >= g.tasks) {
+        if (A.accumulate) {  // idle warp of the last block still takes part in the block reduction
+            const double zero[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            bwd_epilogue(A, zero, gs);
+        }
+        return;
+    }
+
+    // ---- coefficients from the global sums (double once per thread, then fp32) -----------------
+    BwdCoef c;
+    {
+        const double I = gs[0], P = gs[1], T = gs[2];
+        const double s = A.p.smooth, den = P + T + s;
+        double scale = (double)A.grad_scale * (A.upstream ? (double)__ldg(A.upstream) : 1.0);
+        if (KIND == PIL_X_LOGITS_TANH) scale *= 2.0;  // d/dz sigmoid(2z) = 2 u (1-u)
+        const double invN = 1.0 / (A.n_global > 0 ? (double)A.n_global : gs[7]);
+        const bool use_rd = A.p.pde_weight > 0.0, use_pf = A.p.phase_field_weight > 0.0;
+        c.alpha = (float)(scale * A.p.dice_weight * (-2.0 / den));
+        c.beta = (float)(scale * A.p.dice_weight * (2.0 * I + s) / (den * den));
+        c.cb = (float)(scale * A.p.bce_weight * invN);
+        const double crd = use_rd ? scale * A.p.pde_weight * 2.0 * invN : 0.0;
+        c.cA = (float)(crd * A.p.diffusion_coeff);
+        c.f3 = (float)(-3.0 * crd);
+        c.f2 = (float)(2.0 * (1.0 + A.p.reaction_threshold) * crd);
+        c.f1 = (float)(-A.p.reaction_threshold * crd);
+        c.cG = use_pf ? (float)(scale * A.p.phase_field_weight * invN * A.p.epsilon * 0.25) : 0.f;
+        c.cW = use_pf ? (float)(scale * A.p.phase_field_weight * invN * 2.0 / A.p.epsilon) : 0.f;
+        c.D = (float)A.p.diffusion_coeff;
+        c.a1 = (float)(1.0 + A.p.reaction_threshold);
+        c.c0 = (float)(-A.p.reaction_threshold - 4.0 * A.p.diffusion_coeff);
+        c.beta_half = 0.5f * c.beta;
+        c.f1c = (float)(-A.p.reaction_threshold * crd - 4.0 * crd * A.p.diffusion_coeff);
+        c.cW2n = -2.0f * c.cW;
+    }
+
+    // ---- task loop.  Equal static row ranges finish far apart (measured: 83..145 us per block at
+    // 64x1024^2 -- SMs do not get equal shares of the memory system), and with one resident wave nothing
+    // evens that out.  So the ranges are made short and, after its first one, every warp claims the next
+    // unprocessed (range, strip) task from a global counter until none is left.
+    const int H = g.H, W = g.W;
+    const bool out_lane = (lane >= 1) && (lane <= kOutLanes);
+    double tot_r2 = 0.0, tot_g2 = 0.0;  // stencil sums over all tasks of this thread (task partials are fp32)
+    long long task_cur = task;
+#pragma unroll 1
+  for (;;) {
+    int strip;
+    long long pos, end;  // flattened image rows b*H + r of this task
+    decode(task_cur, strip, pos, end);
+    // claim the NEXT task now and pull its first rows into L2, so that the pipeline fill of the next
+    // range costs an L2 round trip instead of a DRAM one (a range is only a few tens of microseconds)
+    const int col0 = strip * kStripCols + (lane - 1) * kVec;
+    const bool in_img = col0 >= 0 && col0 < W;  // ALIGNED: whole vector in the image
+
+    Cols<ALIGNED> cx;
+    cx.init(col0, W);
+    // column factors of the transposed reflect stencils:
+    //   fc: 2 on the first/last image column, 0 outside the image, 1 elsewhere (for r)
+    //   mc: 0 outside the image, 1 inside (for dx)
+    float fc[4], mc[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int cc = col0 + p;
+        const bool in = cc >= 0 && cc < W;
+        mc[p] = in ? 1.0f : 0.0f;
+        fc[p] = in ? ((cc == 0 || cc == W - 1) ? 2.0f : 1.0f) : 0.0f;
+    }
+    // packed path: the same factors folded into per-slot coefficient pairs
+    const f2 cAf2[2] = {make_float2(c.cA * fc[0], c.cA * fc[1]), make_float2(c.cA * fc[2], c.cA * fc[3])};
+    const f2 cGm2[2] = {make_float2(c.cG * mc[0], c.cG * mc[1]), make_float2(c.cG * mc[2], c.cG * mc[3])};
+    const bool store_vec = ALIGNED && out_lane && in_img;
+    // stencil sums of the rows this warp owns (accumulate mode): sum r^2 and sum dx^2+dy^2
+    f2 sr2 = make_float2(0.f, 0.f), sg2 = make_float2(0.f, 0.f);
+    float sr2s = 0.f, sg2s = 0.f;  // scalar path
+
+#pragma unroll 1
+  while (pos < end) {  // one segment per image the range touches (normally one, at most a few)
+    const int b = (int)(pos / H);
+    const int r0 = (int)(pos - (long long)b * H);
+    const int r1 = (int)min((long long)H, (long long)r0 + (end - pos));
+    pos += r1 - r0;
+    const int coff = ALIGNED ? cx.colc : 0;
+    const XT* xb = reinterpret_cast<const XT*>(A.x) + (long long)b * H * W + coff;
+    const TT* tb = reinterpret_cast<const TT*>(A.t) + (long long)b * H * W + coff;
+    XT* gb = reinterpret_cast<XT*>(A.grad) + (long long)b * H * W;  // column added at the store
+    auto xrow = [&](int k) -> const XT* { return xb + (unsigned)(mirror_clamp(k, H) * W); };
+    auto trow = [&](int k) -> const TT* { return tb + (unsigned)(min(k, H - 1) * W); };
+
+    // iteration k forms the residual row k (needs u rows k-1, k, k+1) and emits gradient row k-1.
+    // k runs r0-1 .. r1; u rows r0-2 .. r1+1 are read (mirrored at the image edge).
+    // The u rows and the gradient accumulators live in rings of three that are renamed, not moved, in
+    // the 6x unrolled steady state.  Rows are fetched 5 iterations ahead: through the cp.async stage
+    // ring on the ALIGNED path, through two alternating register slots otherwise.
+    const int k0 = r0 - 1;
+    const float4 xa = cx.template load<XT>(xrow(k0 - 1)), xbq = cx.template load<XT>(xrow(k0));
+    XT* pg = gb + (unsigned)(r0 * W) + (ALIGNED ? col0 : 0);  // next gradient row to store (row k-1)
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 U0, U1, U2;                  // u rows k-1, k, k+1 (the step produces k+1)
+    float4 G0 = zero4, G1 = zero4, G2;  // gradient accumulators of rows k-1, k, k+1
+
+    // compute part of one iteration, given the freshly fetched map row k+1 (xn) and, when a row is
+    // emitted, target row k-1 (tn).  CHECK=false: steady state -- row k strictly inside the image.
+    auto compute_scalar = [&](int k, auto check, const float4& xn, const float4& tn, const float4& ua, const float4& ub,
+                       float4& uc4, float4& gm4, float4& g04, float4& gp4) {
+        constexpr bool CHECK = decltype(check)::value;
+        uc4 = act4<KIND>(cx.fix(xn));  // row k+1
+        const float va[4] = {ua.x, ua.y, ua.z, ua.w};
+        const float vc[4] = {uc4.x, uc4.y, uc4.z, uc4.w};
+        float gm[4] = {gm4.x, gm4.y, gm4.z, gm4.w};
+        float g0[4] = {g04.x, g04.y, g04.z, g04.w};
+        float gp[4];
+        if (!CHECK || (k >= 0 && k < H)) {
+            const float L = __shfl_up_sync(0xffffffffu, ub.w, 1);
+            const float R = __shfl_down_sync(0xffffffffu, ub.x, 1);
+            const float e[6] = {L, ub.x, ub.y, ub.z, ub.w, R};
+            float r[4], rc[4], dx[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float u = e[p + 1];
+                const float s4 = (e[p] + e[p + 2]) + (va[p] + vc[p]);
+                // r = D*(s4 - 4u) + u(1-u)(u-a), as a polynomial in u   (src/pde.py:73-77,:99,:120)
+                r[p] = fmaf(u, fmaf(u, c.a1 - u, c.c0), c.D * s4);
+                rc[p] = r[p];
+                dx[p] = e[p + 2] - e[p];
+            }
+            if (k >= r0 && k < r1) {  // rows this segment owns: the loss terms the light forward skipped
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float w = out_lane ? mc[p] : 0.0f, dy = vc[p] - va[p];
+                    sr2s = fmaf(r[p] * r[p], w, sr2s);
+                    sg2s = fmaf(dx[p] * dx[p] + dy * dy, w, sg2s);
+                }
+            }
+            if constexpr (ALIGNED) {
+                // only slots 0 and 3 can be an image-edge column or feed a neighbour lane; four
+                // unconditional multiplies by per-thread constants (1 everywhere but at the edges)
+                // beat a predicated block, which ptxas expands to 8 issue slots per row in every warp.
+                rc[0] = r[0] * fc[0];
+                rc[3] = r[3] * fc[3];
+                dx[0] *= mc[0];
+                dx[3] *= mc[3];
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    rc[p] *= fc[p];
+                    dx[p] *= mc[p];
+                }
+            }
+            const float rL = __shfl_up_sync(0xffffffffu, rc[3], 1);
+            const float rR = __shfl_down_sync(0xffffffffu, rc[0], 1);
+            const float dL = __shfl_up_sync(0xffffffffu, dx[3], 1);
+            const float dR = __shfl_down_sync(0xffffffffu, dx[0], 1);
+            const float re[6] = {rL, rc[0], rc[1], rc[2], rc[3], rR};
+            const float de[6] = {dL, dx[0], dx[1], dx[2], dx[3], dR};
+            // row factor of the transposed vertical stencil; dy of an edge row is 0 by mirroring
+            const float cAr = (CHECK && (k == 0 || k == H - 1)) ? 2.0f * c.cA : c.cA;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float u = e[p + 1];
+                const float ey = c.cG * (vc[p] - va[p]);
+                gp[p] = fmaf(cAr, r[p], ey);           // into row k+1
+                gm[p] = fmaf(cAr, r[p], gm[p] - ey);   // into row k-1
+                const float fpr = fmaf(u, fmaf(c.f3, u, c.f2), c.f1);  // cF * f'(u)
+                float acc = g0[p];
+                acc = fmaf(c.cA, (re[p] + re[p + 2]) - 4.0f * r[p], acc);
+                acc = fmaf(fpr, r[p], acc);
+                acc = fmaf(c.cG, de[p] - de[p + 2], acc);
+                g0[p] = acc;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) gp[p] = 0.f;
+        }
+        g04 = make_float4(g0[0], g0[1], g0[2], g0[3]);
+        gp4 = make_float4(gp[0], gp[1], gp[2], gp[3]);
+
+        if (!CHECK || k - 1 >= r0) {
+            // emit gradient row k-1 : pointwise terms + accumulated stencil terms, then the chain factor
+            const float vt[4] = {tn.x, tn.y, tn.z, tn.w};
+            float o[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float u = va[p], t = vt[p];
+                const float v = 1.0f - u;
+                const float uv = u * v;
+                float du = gm[p] + fmaf(c.alpha, t, c.beta);
+                du = fmaf(c.cW * uv, v - u, du);
+                if constexpr (KIND == PIL_X_PROB) {
+                    o[p] = fmaf(c.cb * (u - t), rcp_approx(fmaxf(uv, 1e-12f)), du);
+                } else {
+                    // (u-t)/max(uv,1e-12) * uv  ==  (u-t) * sat(uv*1e12)
+                    o[p] = fmaf(du, uv, c.cb * (u - t) * __saturatef(uv * 1e12f));
+                }
+            }
+            if constexpr (ALIGNED) {
+                if (store_vec) st4<XT>(pg, make_float4(o[0], o[1], o[2], o[3]));
+            } else {
+                if (out_lane) {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        if (col0 + p >= 0 && col0 + p < W) st1<XT>(pg + col0 + p, o[p]);
+                }
+            }
+            pg += W;
+        }
+    };
+
+    // Packed (fp32x2) form of the same iteration for the ALIGNED path.  Pairs are (slot0,slot1) and
+    // (slot2,slot3).  The kernel is bound by FMA-pipe cycles (a packed op holds the pipe for two), so the
+    // arithmetic is arranged to minimise them:
+    //   * everything that combines HORIZONTAL neighbours is done with scalar adds on the six values
+    //     {L, s0..s3, R}: a scalar add costs the pipe what half a packed add does, and it avoids the
+    //     register moves that forming misaligned pairs (L,s0) (s1,s2) (s3,R) would need;
+    //   * the transposed horizontal stencils travel as two combined quantities instead of four:
+    //         Ah = cA*fc*r + cG*mc*dx   goes to the RIGHT neighbour,   Bh = cA*fc*r - cG*mc*dx   to the LEFT
+    //     (fc/mc: image-edge column factors, folded into per-slot constants), 2 shuffles instead of 4;
+    //   * the Dice constant beta rides along: Ah and Bh each carry beta/2 and every pixel receives
+    //     exactly one of each, so the emission needs no separate "+ beta";
+    //   * -4*cA*r joins the reaction derivative: (cF f'(u) - 4 cA) * r, one FMA.
+    auto compute_packed = [&](int k, auto check, const float4& xn, const float4& tn, const float4& ua, const float4& ub,
+                              float4& uc4, float4& gm4, float4& g04, float4& gp4) {
+        constexpr bool CHECK = decltype(check)::value;
+        uc4 = act4<KIND>(cx.fix(xn));  // row k+1
+        const f2 va[2] = {make_float2(ua.x, ua.y), make_float2(ua.z, ua.w)};
+        const f2 vc[2] = {make_float2(uc4.x, uc4.y), make_float2(uc4.z, uc4.w)};
+        f2 gm[2] = {make_float2(gm4.x, gm4.y), make_float2(gm4.z, gm4.w)};
+        f2 g0[2] = {make_float2(g04.x, g04.y), make_float2(g04.z, g04.w)};
+        f2 gp[2];
+        if (!CHECK || (k >= 0 && k < H)) {
+            const float L = __shfl_up_sync(0xffffffffu, ub.w, 1);
+            const float R = __shfl_down_sync(0xffffffffu, ub.x, 1);
+            const f2 u[2] = {make_float2(ub.x, ub.y), make_float2(ub.z, ub.w)};
+            // horizontal neighbour sums and differences, scalar (src/pde.py:73-77, :172)
+            const f2 hs[2] = {make_float2(L + ub.y, ub.x + ub.z), make_float2(ub.y + ub.w, ub.z + R)};
+            const f2 dx[2] = {make_float2(ub.y - L, ub.z - ub.x), make_float2(ub.w - ub.y, R - ub.z)};
+            f2 r[2], dy[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const f2 s4 = add2(hs[h], add2(va[h], vc[h]));
+                // r = D*(s4 - 4u) + u(1-u)(u-a), as a polynomial in u   (src/pde.py:73-77,:99,:120)
+                r[h] = fma2(u[h], fma2(u[h], sub2(bc(c.a1), u[h]), bc(c.c0)), mul2(bc(c.D), s4));
+                dy[h] = sub2(vc[h], va[h]);
+            }
+            if (!CHECK || (k >= r0 && k < r1)) {  // rows this segment owns: loss terms the light forward skipped
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    sr2 = fma2(r[h], r[h], sr2);
+                    sg2 = fma2(dx[h], dx[h], sg2);
+                    sg2 = fma2(dy[h], dy[h], sg2);
+                }
+            }
+            // row factor of the transposed vertical stencil; dy of an edge row is 0 by mirroring
+            const float cAr = (CHECK && (k == 0 || k == H - 1)) ? 2.0f * c.cA : c.cA;
+            f2 Ah[2], Bh[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const f2 qv = mul2(bc(cAr), r[h]);
+                gp[h] = fma2(bc(c.cG), dy[h], qv);                     // into row k+1:  cA r + cG dy
+                gm[h] = add2(gm[h], fma2(bc(-c.cG), dy[h], qv));       // into row k-1:  cA r - cG dy
+                const f2 qf = fma2(cAf2[h], r[h], bc(c.beta_half));
+                Ah[h] = fma2(cGm2[h], dx[h], qf);
+                Bh[h] = fma2(make_float2(-cGm2[h].x, -cGm2[h].y), dx[h], qf);
+            }
+            const float AL = __shfl_up_sync(0xffffffffu, Ah[1].y, 1);    // from the pixel left of slot 0
+            const float BR = __shfl_down_sync(0xffffffffu, Bh[0].x, 1);  // from the pixel right of slot 3
+            const f2 hg[2] = {make_float2(AL + Bh[0].y, Ah[0].x + Bh[1].x), make_float2(Ah[0].y + Bh[1].y, Ah[1].x + BR)};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const f2 fpr = fma2(u[h], fma2(bc(c.f3), u[h], bc(c.f2)), bc(c.f1c));  // cF f'(u) - 4 cA
+                g0[h] = fma2(fpr, r[h], add2(g0[h], hg[h]));
+            }
+        } else {
+            gp[0] = gp[1] = make_float2(0.f, 0.f);
+        }
+        g04 = make_float4(g0[0].x, g0[0].y, g0[1].x, g0[1].y);
+        gp4 = make_float4(gp[0].x, gp[0].y, gp[1].x, gp[1].y);
+
+        if (!CHECK || k - 1 >= r0) {
+            // emit gradient row k-1 : pointwise terms + accumulated stencil terms (beta included), chain factor
+            const f2 vt[2] = {make_float2(tn.x, tn.y), make_float2(tn.z, tn.w)};
+            f2 o[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const f2 u = va[h], t = vt[h];
+                const f2 v = sub2(bc(1.0f), u);
+                const f2 uv = mul2(u, v);
+                // du = gm + alpha t + cW uv (1-2u)
+                const f2 du = fma2(uv, fma2(bc(c.cW2n), u, bc(c.cW)), fma2(bc(c.alpha), t, gm[h]));
+                const f2 w = mul2(bc(c.cb), sub2(u, t));
+                if constexpr (KIND == PIL_X_PROB) {
+                    const f2 inv = make_float2(rcp_approx(fmaxf(uv.x, 1e-12f)), rcp_approx(fmaxf(uv.y, 1e-12f)));
+                    o[h] = fma2(w, inv, du);
+                } else {
+                    // (u-t)/max(uv,1e-12) * uv  ==  (u-t) * sat(uv*1e12)
+                    const f2 m = make_float2(__saturatef(uv.x * 1e12f), __saturatef(uv.y * 1e12f));
+                    o[h] = fma2(du, uv, mul2(w, m));
+                }
+            }
+            if (store_vec) st4<XT>(pg, make_float4(o[0].x, o[0].y, o[1].x, o[1].y));
+            pg += W;
+        }
+    };
+    auto compute = [&](int k, auto check, const float4& xn, const float4& tn, const float4& ua, const float4& ub,
+                       float4& uc4, float4& gm4, float4& g04, float4& gp4) {
+        if constexpr (ALIGNED) {
+            compute_packed(k, check, xn, tn, ua, ub, uc4, gm4, g04, gp4);
+        } else {
+            compute_scalar(k, check, xn, tn, ua, ub, uc4, gm4, g04, gp4);
+        }
+    };
+
+    if constexpr (ALIGNED) {
+        // ---- staged path: iteration k consumes stage (k-k0)%6 = {map row k+1, target row k-1} ----
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        StageRing<XT, TT> ring;
+        ring.init(smem_raw, warp, lane);
+        const XT* px = xb + (long long)(k0 + 1) * W;  // map row of the next iteration to be issued
+        const TT* pt = tb + (long long)(k0 - 1) * W;  // target row of the next iteration to be issued
+        auto issue = [&](int j, int stage, auto check) {
+            constexpr bool CHECK = decltype(check)::value;
+            if constexpr (CHECK) {
+                if (j + 1 <= min(r1 + 1, H)) ring.issue_x(stage, (j + 1 == H) ? px - 2 * W : px);  // row H := row H-2
+                if (j - 1 >= r0 && j - 1 < r1) ring.issue_t(stage, pt);
+            } else {
+                ring.issue_x(stage, px);
+                ring.issue_t(stage, pt);
+            }
+            px += W;
+            pt += W;
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int q = 0; q < kStages - 1; ++q) issue(k0 + q, q, BoolC<true>{});
+        U0 = act4<KIND>(cx.fix(xa));   // row k0-1
+        U1 = act4<KIND>(cx.fix(xbq));  // row k0
+
+        auto step = [&](int k, int stage, auto check, const float4& ua, const float4& ub, float4& uc4, float4& gm4,
+                        float4& g04, float4& gp4) {
+            issue(k + kStages - 1, (stage + kStages - 1) % kStages, check);
+            cp_async_wait<kStages - 1>();
+            const float4 xn = ring.read_x(stage), tn = ring.read_t(stage);
+            compute(k, check, xn, tn, ua, ub, uc4, gm4, g04, gp4);
+        };
+        int k = k0, stage = 0;
+        auto rot_step = [&](int kk) {
+            step(kk, stage, BoolC<true>{}, U0, U1, U2, G0, G1, G2);
+            stage = (stage + 1 == kStages) ? 0 : stage + 1;
+            U0 = U1;
+            U1 = U2;
+            G0 = G1;
+            G1 = G2;
+        };
+        rot_step(k++);  // k = r0-1: forms r[r0-1], emits nothing
+        rot_step(k++);  // k = r0  : forms r[r0],   emits nothing
+        // steady state: compute clean for k in [r0+1, r1-4]; issue (k+5) clean for k+5 <= r1-2
+#pragma unroll 1
+        for (; k + 5 <= r1 - 7; k += kStages) {
+            step(k + 0, 2, BoolC<false>{}, U0, U1, U2, G0, G1, G2);
+            step(k + 1, 3, BoolC<false>{}, U1, U2, U0, G1, G2, G0);
+            step(k + 2, 4, BoolC<false>{}, U2, U0, U1, G2, G0, G1);
+            step(k + 3, 5, BoolC<false>{}, U0, U1, U2, G0, G1, G2);
+            step(k + 4, 0, BoolC<false>{}, U1, U2, U0, G1, G2, G0);
+            step(k + 5, 1, BoolC<false>{}, U2, U0, U1, G2, G0, G1);
+        }
+#pragma unroll 1
+        for (; k <= r1; ++k) rot_step(k);
+        cp_async_wait<0>();
+    } else {
+        // ---- register path (scalar loads): two alternating fetch slots, two rows ahead ----
+        float4 xA = cx.template load<XT>(xrow(k0 + 1));   // row k+1 of the first iteration
+        float4 xB = cx.template load<XT>(xrow(k0 + 2));
+        float4 tA = cx.template load_plain<TT>(trow(r0));  // consumed when row r0 is emitted (k = r0+1)
+        float4 tB = cx.template load_plain<TT>(trow(r0 + 1));
+        U0 = act4<KIND>(cx.fix(xa));
+        U1 = act4<KIND>(cx.fix(xbq));
+        const XT* px = xb + (unsigned)((k0 + 3) * W);  // next map row to fetch (row k+3)
+        const TT* pt = tb + (unsigned)((r0 + 2) * W);  // next target row to fetch
+#pragma unroll 1
+        for (int k = k0; k <= r1; ++k) {
+            const float4 xn = xA, tn = tA;
+            if (k + 3 <= min(r1 + 1, H)) xA = cx.template load<XT>((k + 3 == H) ? px - 2 * W : px);
+            px += W;
+            const bool emits = k - 1 >= r0;
+            if (emits) {
+                if (k + 1 < r1) tA = cx.template load_plain<TT>(pt);
+                pt += W;
+            }
+            compute(k, BoolC<true>{}, xn, tn, U0, U1, U2, G0, G1, G2);
+            float4 sw = xA;
+            xA = xB;
+            xB = sw;
+            if (emits) {
+                sw = tA;
+                tA = tB;
+                tB = sw;
+            }
+            U0 = U1;
+            U1 = U2;
+            G0 = G1;
+            G1 = G2;
+        }
+    }
+  }  // segments
+
+    if constexpr (ALIGNED) {
+        if (store_vec) {
+            tot_r2 += (double)(sr2.x + sr2.y);
+            tot_g2 += (double)(sg2.x + sg2.y);
+        }
+    } else {
+        tot_r2 += (double)sr2s;
+        tot_g2 += (double)sg2s;
+    }
+    // claim the next unprocessed task.  (Claiming earlier -- to prefetch the next range -- was measured
+    // to lose more than it gains: a task held in reserve is not available to a warp that runs dry.)
+    if (A.task_counter == nullptr) break;
+    unsigned int claimed = 0u;
+    if (lane == 0) claimed = atomicAdd(A.task_counter, 1u);
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    task_cur = A.first_dynamic + (long long)claimed;
+    if (task_cur >= g.tasks) break;
+  }  // tasks
+
+    TL_STAMP(1, 2);
+    if (!A.accumulate) return;  // uniform: plain pil_backward
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    acc[4] = tot_r2;
+    acc[5] = tot_g2;
+    bwd_epilogue(A, acc, gs);
+    TL_STAMP(1, 3);
+}
+// Rows per dynamically claimed range of the backward kernel.  PIL_BWD_ROWS forces a value (0 = static
+// partition).  Automatic: 64 rows -- long enough to amortise the 4 halo rows and the pipeline fill of a
+// range, short enough to balance.  Measured on B200 at 64x1024^2 fp32: static 157.8 us; dynamic 24 rows
+// 169.9, 32: 157.5, 48: 155.6, 61: 149-153, 63: 150.5, 64: 145-147, 67: 152, 96: 149.5, 128: 155.7 (the
+// power of two wins over its neighbours: range boundaries then tile the 2 MB pages).  Shrinking ranges
+// (guided self-scheduling), a small-range tail phase and claiming one range ahead to prefetch it were all
+// measured slower.  Problems too small for ~2.5 waves of such ranges keep the static one-wave partition.
+static int bwd_dynamic_rows(long long total_rows, long long strips, long long resident_warps) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("PIL_BWD_ROWS");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0) return (forced > 0 && forced < kMinRows) ? kMinRows : forced;
+    const int rows = 64;
+    const double waves = (double)(((total_rows + rows - 1) / rows) * strips) / (double)resident_warps;
+    return waves < 2.5 ? 0 : rows;
+}
+template <int KIND, typename XT, typename TT>
+static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned, cudaStream_t s, LaunchOut* out) {
+    static std::atomic<int> per_sm_cache[2][kMaxDevices];  // per template instantiation x {scalar, aligned} kernel x device
+    auto go = [&](auto kernel, int smem) -> cudaError_t {
+        const int per_sm = blocks_per_sm_cached(kernel, kThreads, smem, per_sm_cache[aligned ? 1 : 0], true);
+        const int tune_rps = host_state().tune_bwd_rps.load();
+        const int resident = sm_count() * per_sm;
+        const long long strips_ = (W + kStripCols - 1) / kStripCols;
+        const int dyn_rows = a.task_counter != nullptr
+                                 ? (tune_rps > 0 ? tune_rps : bwd_dynamic_rows(B * H, strips_, (long long)resident * kWarpsPerBlock))
+                                 : 0;
+        if (dyn_rows > 0) {
+            // persistent grid of the resident blocks; short ranges claimed dynamically (see the kernel)
+            a.g = make_geo(B, H, W, resident, dyn_rows, 1);
+            const long long need = (a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+            out->blocks = (int)(need < resident ? need : resident);
+            a.first_dynamic = (long long)out->blocks * kWarpsPerBlock;
+        } else {
+            a.task_counter = nullptr;
+            a.first_dynamic = 0;
+            a.g = make_geo(B, H, W, resident, tune_rps, tuning_waves(true, B, H, W, resident));
+            out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        }
+        out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
+        if (a.accumulate && (size_t)out->blocks * PIL_NSUMS * sizeof(double) > out->partials_avail) {
+            out->status = PIL_ERR_WORKSPACE;
+            return cudaSuccess;
+        }
+        return launch_pdl(kernel, out->blocks, kThreads, smem, s, a);
+    };
+    if (aligned) return go(pil_bwd_kernel<KIND, XT, TT, true>, kSmemPerBlock);
+    return go(pil_bwd_kernel<KIND, XT, TT, false>, 0);
+}
+#define PIL_BWD_ARGS BwdArgs &a, int64_t B, int64_t H, int64_t W, bool aligned, cudaStream_t s, LaunchOut *out
+#define PIL_BWD_PASS a, B, H, W, aligned, s, out
+template <int KIND, typename XT>
+static cudaError_t launch_bwd_t(int t_dtype, PIL_BWD_ARGS) {
+#ifdef PIL_DEV_F32_ONLY  // development builds: fp32 maps only (6x faster to compile)
+    if (t_dtype != PIL_F32) return cudaErrorNotSupported;
+    return launch_bwd_a<KIND, XT, float>(PIL_BWD_PASS);
+#else
+    switch (t_dtype) {
+        case PIL_F32: return launch_bwd_a<KIND, XT, float>(PIL_BWD_PASS);
+        case PIL_BF16: return launch_bwd_a<KIND, XT, __nv_bfloat16>(PIL_BWD_PASS);
+        default: return launch_bwd_a<KIND, XT, uint8_t>(PIL_BWD_PASS);
+    }
+#endif
+}
+template <int KIND>
+static cudaError_t launch_bwd_x(int x_dtype, int t_dtype, PIL_BWD_ARGS) {
+    if (x_dtype == PIL_F32) return launch_bwd_t<KIND, float>(t_dtype, PIL_BWD_PASS);
+#ifdef PIL_DEV_F32_ONLY
+    return cudaErrorNotSupported;
+#else
+    return launch_bwd_t<KIND, __nv_bfloat16>(t_dtype, PIL_BWD_PASS);
+#endif
+}
+
+// exported to pil_api.cu: one entry per input kind
+#if !defined(PIL_KIND) || PIL_KIND == 0
+cudaError_t launch_bwd_k0(int x_dtype, int t_dtype, PIL_BWD_ARGS) { return launch_bwd_x<PIL_X_PROB>(x_dtype, t_dtype, PIL_BWD_PASS); }
+#endif
+#if !defined(PIL_KIND) || PIL_KIND == 1
+cudaError_t launch_bwd_k1(int x_dtype, int t_dtype, PIL_BWD_ARGS) { return launch_bwd_x<PIL_X_LOGITS_SIGMOID>(x_dtype, t_dtype, PIL_BWD_PASS); }
+#endif
+#if !defined(PIL_KIND) || PIL_KIND == 2
+cudaError_t launch_bwd_k2(int x_dtype, int t_dtype, PIL_BWD_ARGS) { return launch_bwd_x<PIL_X_LOGITS_TANH>(x_dtype, t_dtype, PIL_BWD_PASS); }
+#endif
+
+}  // namespace pil

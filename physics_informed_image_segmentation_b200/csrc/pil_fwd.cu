@@ -1,0 +1,272 @@
+// pil_fwd.cu -- K1, the fused full forward kernel (validation / no-grad path and the parameter-sweep moments),
+// and its launcher.  Compiled once per input kind (-DPIL_KIND=0|1|2) so the instantiations build in parallel;
+// without PIL_KIND (unity development builds) all three kinds are instantiated here.
+#include "pil_fwdrow.cuh"
+
+namespace pil {
+template <int KIND, typename XT, typename TT, bool ALIGNED, bool MOMENTS>
+__global__ void __launch_bounds__(kThreads, MOMENTS ? kFwdMinBlocks - 1 : kFwdMinBlocks) pil_fwd_kernel(const FwdArgs A) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Geo& g = A.g;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
+
+    constexpr int NACC = MOMENTS ? 16 : 8;
+    FwdRow<KIND, ALIGNED, MOMENTS> fr;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) fr.acc[k] = 0.f;
+    fr.init_packed();
+    fr.D = A.D;
+    fr.a = A.a;
+    fr.a1 = 1.0f + A.a;
+    fr.c0 = -A.a - 4.0f * A.D;
+
+    if (task < g.tasks) {
+        const int strip = (int)(task % g.strips);
+        const long long grp = task / g.strips;
+        long long pos = (g.total_rows * grp) / g.groups;              // flattened image row b*H + r
+        const long long end = (g.total_rows * (grp + 1)) / g.groups;
+        const int H = g.H, W = g.W;
+        const int col0 = strip * kStripCols + (lane - 1) * kVec;
+        const bool out_lane = (lane >= 1) && (lane <= kOutLanes);
+        const bool counted = out_lane && col0 >= 0 && col0 < W;  // ALIGNED: all 4 slots are real pixels
+
+        Cols<ALIGNED> cx;
+        cx.init(col0, W);
+        if constexpr (!ALIGNED) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) fr.m[p] = (out_lane && col0 + p >= 0 && col0 + p < W) ? 1.0f : 0.0f;
+        }
+#pragma unroll 1
+      while (pos < end) {  // one segment per image the range touches (normally one, at most a few)
+        const int b = (int)(pos / H);
+        const int r0 = (int)(pos - (long long)b * H);
+        const int r1 = (int)min((long long)H, (long long)r0 + (end - pos));
+        pos += r1 - r0;
+
+        // per-image base pointers at this thread's column; rows are addressed with 32-bit offsets
+        const int coff = ALIGNED ? cx.colc : 0;
+        const XT* xb = reinterpret_cast<const XT*>(A.x) + (long long)b * H * W + coff;
+        const TT* tb = reinterpret_cast<const TT*>(A.t) + (long long)b * H * W + coff;
+        auto xrow = [&](int k) -> const XT* { return xb + (unsigned)(mirror_clamp(k, H) * W); };
+        auto trow = [&](int k) -> const TT* { return tb + (unsigned)(min(k, H - 1) * W); };
+
+        if constexpr (ALIGNED) {
+            // ---- staged path: iteration i consumes stage (i-r0)%6 = {map row i+1, target row i+1} ----
+            // It activates row i+1 and adds that row's per-pixel terms (if the segment owns it), then adds
+            // the stencil terms of row i, whose three u rows are now all in registers.
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            StageRing<XT, TT> ring;
+            ring.init(smem_raw, warp, lane);
+            const XT* px = xb + (unsigned)((r0 + 1) * W);  // map row of the next iteration to be issued
+            const TT* pt = tb + (unsigned)((r0 + 1) * W);  // target row of the next iteration to be issued
+            // issue(j): the copies iteration j will consume; CHECK handles the segment/image end
+            auto issue = [&](int j, int stage, auto check) {
+                constexpr bool CHECK = decltype(check)::value;
+                if constexpr (CHECK) {
+                    if (j < r1) ring.issue_x(stage, (j + 1 == H) ? px - 2 * W : px);  // row H := row H-2 (mirror)
+                    if (j + 1 < r1) ring.issue_t(stage, pt);
+                } else {
+                    ring.issue_x(stage, px);
+                    ring.issue_t(stage, pt);
+                }
+                px += W;
+                pt += W;
+                cp_async_commit();
+            };
+            const float4 x0 = cx.template load<XT>(xrow(r0 - 1)), x1 = cx.template load<XT>(xrow(r0));
+            const float4 t1 = cx.template load_plain<TT>(trow(r0));
+#pragma unroll
+            for (int q = 0; q < kStages - 1; ++q) issue(r0 + q, q, BoolC<true>{});
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 U0 = fr.point4(cx.fix(x0), zero4, false);  // row r0-1: halo row, contributes no pixel terms
+            float4 U1 = fr.point4(cx.fix(x1), t1, true);      // row r0
+            float4 U2;
+
+            auto step = [&](int i, int stage, auto check, const float4& um, const float4& uc, float4& up) {
+                constexpr bool CHECK = decltype(check)::value;
+                issue(i + kStages - 1, (stage + kStages - 1) % kStages, check);
+                cp_async_wait<kStages - 1>();
+                const float4 xn = ring.read_x(stage), tn = ring.read_t(stage);
+                up = fr.point4(cx.fix(xn), tn, !CHECK || (i + 1 < r1));
+                fr.stencil4(um, uc, up);
+            };
+            int i = r0;
+            // steady state: the issue of iteration i+5+5 must stay clean -> i + 11 <= r1 - 2
+#pragma unroll 1
+            for (; i + 2 * kStages <= r1 - 1; i += kStages) {
+                step(i + 0, 0, BoolC<false>{}, U0, U1, U2);
+                step(i + 1, 1, BoolC<false>{}, U1, U2, U0);
+                step(i + 2, 2, BoolC<false>{}, U2, U0, U1);
+                step(i + 3, 3, BoolC<false>{}, U0, U1, U2);
+                step(i + 4, 4, BoolC<false>{}, U1, U2, U0);
+                step(i + 5, 5, BoolC<false>{}, U2, U0, U1);
+            }
+            int stage = 0;
+#pragma unroll 1
+            for (; i < r1; ++i) {  // segment tail (and short segments): dynamic stage, explicit rotation
+                step(i, stage, BoolC<true>{}, U0, U1, U2);
+                stage = (stage + 1 == kStages) ? 0 : stage + 1;
+                U0 = U1;
+                U1 = U2;
+            }
+            cp_async_wait<0>();
+        } else {
+            // prologue: rows r0-1, r0 become u; rows r0+1, r0+2 and targets r0, r0+1 are in flight.
+            // Two fetch slots (A,B) alternate: iteration i consumes the slot holding map row i+1 / target
+            // row i and immediately refills it with rows i+3 / i+2, so loaded registers are never moved
+            // (a MOV of a loaded register would stall on the load and defeat the prefetch).
+            const float4 x0 = cx.template load<XT>(xrow(r0 - 1)), x1 = cx.template load<XT>(xrow(r0));
+            float4 xA = cx.template load<XT>(xrow(r0 + 1));
+            float4 xB = cx.template load<XT>(xrow(min(r0 + 2, r1)));
+            float4 tA = cx.template load_plain<TT>(trow(r0));
+            float4 tB = cx.template load_plain<TT>(trow(r0 + 1));
+            float4 U0 = act4<KIND>(cx.fix(x0)), U1 = act4<KIND>(cx.fix(x1)), U2;
+            const XT* px = xb + (unsigned)((r0 + 3) * W);  // next map row to fetch (row i+3)
+            const TT* pt = tb + (unsigned)((r0 + 2) * W);  // next target row to fetch (row i+2)
+
+            // CHECK=false: steady state, every fetched row is inside the segment and the image.
+            auto step = [&](int i, auto check, float4& xs, float4& ts, const float4& um, const float4& uc, float4& up) {
+                constexpr bool CHECK = decltype(check)::value;
+                const float4 xn = xs, tn = ts;
+                if constexpr (CHECK) {
+                    if (i + 3 <= r1) xs = cx.template load<XT>((i + 3 == H) ? px - 2 * W : px);  // row H := row H-2
+                    if (i + 2 < r1) ts = cx.template load_plain<TT>(pt);
+                } else {
+                    xs = cx.template load<XT>(px);
+                    ts = cx.template load_plain<TT>(pt);
+                }
+                px += W;
+                pt += W;
+                up = act4<KIND>(cx.fix(xn));
+                fr.row(um, uc, up, tn);
+            };
+            int i = r0;
+#pragma unroll 1
+            for (; i + 6 <= r1 - 3; i += 6) {
+                step(i + 0, BoolC<false>{}, xA, tA, U0, U1, U2);
+                step(i + 1, BoolC<false>{}, xB, tB, U1, U2, U0);
+                step(i + 2, BoolC<false>{}, xA, tA, U2, U0, U1);
+                step(i + 3, BoolC<false>{}, xB, tB, U0, U1, U2);
+                step(i + 4, BoolC<false>{}, xA, tA, U1, U2, U0);
+                step(i + 5, BoolC<false>{}, xB, tB, U2, U0, U1);
+            }
+#pragma unroll 1
+            for (; i < r1; ++i) {  // segment tail (and short segments): same step, explicit rotation
+                step(i, BoolC<true>{}, xA, tA, U0, U1, U2);
+                float4 sw = xA;
+                xA = xB;
+                xB = sw;
+                sw = tA;
+                tA = tB;
+                tB = sw;
+                U0 = U1;
+                U1 = U2;
+            }
+
+        }
+      }  // segments
+
+        if constexpr (ALIGNED) {
+            fr.fold_packed();
+            if (!counted) {
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) fr.acc[k] = 0.f;
+            }
+        }
+    }
+
+    // ---- deterministic cross-block reduction; the last block finalises --------------------------
+    if constexpr (MOMENTS) {
+        double raw[16];
+        if (!reduce_to_last_block<kThreads, float, 16>(fr.acc, A.partials, A.ticket, raw)) return;
+        if (threadIdx.x == 0) {  // layout: include/pil.h PIL_NMOMENTS
+            double* mo = A.sums;
+            mo[0] = raw[0];
+            mo[1] = raw[1];
+            mo[2] = raw[2];
+            mo[3] = -(double)kLn2 * raw[3];
+            mo[4] = raw[4];            // sum lap^2
+            mo[5] = 0.25 * raw[5];     // sum gx^2 + gy^2
+            mo[6] = raw[6];            // sum g^2 = sum u^2 (1-u)^2
+            mo[7] = raw[7];            // n_invalid
+            mo[8] = raw[8];            // sum lap*h
+            mo[9] = raw[9];            // sum lap*g
+            mo[10] = raw[10];          // sum h^2
+            mo[11] = raw[11];          // sum h*g
+            mo[12] = (double)g.B * (double)g.H * (double)g.W;
+            mo[13] = mo[14] = mo[15] = 0.0;
+            *A.ticket = 0u;
+        }
+        return;
+    }
+    double raw[PIL_NSUMS];
+    if (!reduce_to_last_block<kThreads, float>(fr.acc, A.partials, A.ticket, raw)) return;
+    if (threadIdx.x == 0) {
+        double s[PIL_NSUMS];
+        sums_from_raw(raw, A.p.epsilon, (double)g.B * (double)g.H * (double)g.W, s);
+#pragma unroll
+        for (int k = 0; k < PIL_NSUMS; ++k) A.sums[k] = s[k];
+        if (A.loss_out != nullptr) finalize_device(s, s[7], A.p, A.loss_out);
+        *A.ticket = 0u;
+    }
+}
+template <int KIND, typename XT, typename TT>
+static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned, size_t partial_bytes_avail,
+                                cudaStream_t s, LaunchOut* out, bool moments) {
+    static std::atomic<int> per_sm_cache[4][kMaxDevices];  // per template instantiation x {scalar, aligned} x {sums, moments} x device
+    auto go = [&](auto kernel, int smem) -> cudaError_t {
+        const int per_sm = blocks_per_sm_cached(kernel, kThreads, smem, per_sm_cache[(aligned ? 1 : 0) + (moments ? 2 : 0)], true);
+        a.g = make_geo(B, H, W, sm_count() * per_sm, host_state().tune_fwd_rps.load(), tuning_waves(false, B, H, W, sm_count() * per_sm));
+        out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
+        if ((size_t)out->blocks * (moments ? 16 : PIL_NSUMS) * sizeof(double) > partial_bytes_avail) {
+            out->status = PIL_ERR_WORKSPACE;
+            return cudaSuccess;
+        }
+        kernel<<<out->blocks, kThreads, smem, s>>>(a);
+        return cudaGetLastError();
+    };
+    if (moments) {
+        if (aligned) return go(pil_fwd_kernel<KIND, XT, TT, true, true>, kSmemPerBlock);
+        return go(pil_fwd_kernel<KIND, XT, TT, false, true>, 0);
+    }
+    if (aligned) return go(pil_fwd_kernel<KIND, XT, TT, true, false>, kSmemPerBlock);
+    return go(pil_fwd_kernel<KIND, XT, TT, false, false>, 0);
+}
+#define PIL_FWD_ARGS FwdArgs &a, int64_t B, int64_t H, int64_t W, bool aligned, size_t avail, cudaStream_t s, LaunchOut *out, bool moments
+#define PIL_FWD_PASS a, B, H, W, aligned, avail, s, out, moments
+template <int KIND, typename XT>
+static cudaError_t launch_fwd_t(int t_dtype, PIL_FWD_ARGS) {
+#ifdef PIL_DEV_F32_ONLY  // development builds: fp32 maps only (6x faster to compile)
+    if (t_dtype != PIL_F32) return cudaErrorNotSupported;
+    return launch_fwd_a<KIND, XT, float>(PIL_FWD_PASS);
+#else
+    switch (t_dtype) {
+        case PIL_F32: return launch_fwd_a<KIND, XT, float>(PIL_FWD_PASS);
+        case PIL_BF16: return launch_fwd_a<KIND, XT, __nv_bfloat16>(PIL_FWD_PASS);
+        default: return launch_fwd_a<KIND, XT, uint8_t>(PIL_FWD_PASS);
+    }
+#endif
+}
+template <int KIND>
+static cudaError_t launch_fwd_x(int x_dtype, int t_dtype, PIL_FWD_ARGS) {
+    if (x_dtype == PIL_F32) return launch_fwd_t<KIND, float>(t_dtype, PIL_FWD_PASS);
+#ifdef PIL_DEV_F32_ONLY
+    return cudaErrorNotSupported;
+#else
+    return launch_fwd_t<KIND, __nv_bfloat16>(t_dtype, PIL_FWD_PASS);
+#endif
+}
+
+// exported to pil_api.cu: one entry per input kind (each lives in its own translation unit in release builds)
+#if !defined(PIL_KIND) || PIL_KIND == 0
+cudaError_t launch_fwd_k0(int x_dtype, int t_dtype, PIL_FWD_ARGS) { return launch_fwd_x<PIL_X_PROB>(x_dtype, t_dtype, PIL_FWD_PASS); }
+#endif
+#if !defined(PIL_KIND) || PIL_KIND == 1
+cudaError_t launch_fwd_k1(int x_dtype, int t_dtype, PIL_FWD_ARGS) { return launch_fwd_x<PIL_X_LOGITS_SIGMOID>(x_dtype, t_dtype, PIL_FWD_PASS); }
+#endif
+#if !defined(PIL_KIND) || PIL_KIND == 2
+cudaError_t launch_fwd_k2(int x_dtype, int t_dtype, PIL_FWD_ARGS) { return launch_fwd_x<PIL_X_LOGITS_TANH>(x_dtype, t_dtype, PIL_FWD_PASS); }
+#endif
+
+}  // namespace pil
