@@ -231,12 +231,19 @@ int pil_sweep_finalize(const double* moments, int64_t n_global, const PilParams*
  * pil_exchange_open; mailbox[rank] is the rank's own pointer.  Per step all ranks pass the SAME
  * `epoch`, incremented by one every step, and run the two calls in this order on one stream.
  * Every rank must own its GPU: the kernels wait on flags written by kernels of other ranks.
- * A wait that exceeds PIL_XCHG_TIMEOUT_MS (default 20000) gives up: the loss report becomes NaN and
- * the mailbox status word (pil_exchange_status) is set.
+ * A wait that exceeds PIL_XCHG_TIMEOUT_MS (default 20000) gives up: the loss report becomes NaN, the rank's
+ * gradient is written as ZEROS (a rank that lost its peers must not poison the weights) and the mailbox
+ * status word (pil_exchange_status) is set.
  */
 #define PIL_MAX_RANKS 8
 #define PIL_IPC_HANDLE_BYTES 64
 #define PIL_XCHG_DEFER_FINALIZE 1u /* the backward only pushes its stencil sums; pil_exchange_finalize assembles the loss */
+/* The step tag comes from a counter in the rank's own mailbox instead of `epoch`: the backward's last block
+ * increments it when the step is complete.  The two launches of a step then take identical arguments every
+ * step, so they can be captured once in a CUDA graph (pil_step_graph_*).  All ranks must use the same mode for
+ * the lifetime of a mailbox, and pil_forward_pointwise_xchg must always be followed by its
+ * pil_backward_accumulate_xchg.  Not combinable with PIL_XCHG_DEFER_FINALIZE. */
+#define PIL_XCHG_DEVICE_EPOCH 2u
 typedef struct PilExchange {
     int32_t rank, world;
     uint64_t epoch;
@@ -313,6 +320,10 @@ int pil_last_launch_info(PilLaunchInfo* out);
 
 /* Tuning override for benchmarks (0 = automatic): rows per segment for fwd / bwd. */
 int pil_set_tuning(int fwd_rows_per_segment, int bwd_rows_per_segment);
+/* How the aligned backward kernel stages its rows in shared memory: 1 = TMA boxes (cp.async.bulk.tensor, one
+ * elected lane per warp, mbarrier completion), 0 = one cp.async per lane per row, negative = default
+ * (PIL_BWD_STAGE=tma|cpasync, else the library's choice).  PilLaunchInfo.bwd_aligned reports 2 for TMA. */
+int pil_set_bwd_staging(int mode);
 /* How many MB at the end of each fp32 map the pointwise forward asks L2 to keep (evict_last) for the backward
  * kernel, which starts there; the rest of its stream is evict_first.  0 = plain loads; negative = default
  * (PIL_L2_KEEP_MB or 12). */

@@ -63,6 +63,7 @@ class PilLaunchInfo(ctypes.Structure):
 PIL_MAX_RANKS = 8
 PIL_IPC_HANDLE_BYTES = 64
 PIL_XCHG_DEFER_FINALIZE = 1
+PIL_XCHG_DEVICE_EPOCH = 2
 PIL_SESSION_GRAD_ON_DEVICE = 1
 
 
@@ -204,6 +205,7 @@ _SIGS = {
     "pil_last_launch_info": (ctypes.c_int, [ctypes.POINTER(PilLaunchInfo)]),
     "pil_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "pil_set_l2_keep_mb": (ctypes.c_int, [ctypes.c_int]),
+    "pil_set_bwd_staging": (ctypes.c_int, [ctypes.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -178,6 +178,38 @@ int sm_count() {
     }
     return n;
 }
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (libpil.so links cudart only)
+bool make_tensor_map_2d(CUtensorMap* out, const void* base, int dtype, long long rows, long long cols, int box_rows, int box_cols) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static std::atomic<EncodeFn> cached{nullptr};
+    static std::atomic<int> tried{0};
+    EncodeFn fn = cached.load(std::memory_order_acquire);
+    if (fn == nullptr) {
+        if (tried.load(std::memory_order_acquire)) return false;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess && p != nullptr) {
+            fn = reinterpret_cast<EncodeFn>(p);
+            cached.store(fn, std::memory_order_release);
+        }
+        tried.store(1, std::memory_order_release);
+        if (fn == nullptr) return false;
+    }
+    const size_t esz = dtype_size(dtype);
+    if (((uintptr_t)base % 16) || ((size_t)cols * esz) % 16 || rows < 1 || cols < 1 || rows >= (1ll << 31) - 64) return false;
+    const CUtensorMapDataType dt = dtype == PIL_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                    : (dtype == PIL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * esz};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static unsigned long long xchg_timeout_ns() {
     static unsigned long long v = 0;
     if (v == 0) {
@@ -195,6 +227,8 @@ static int make_xchg(const PilExchange* ex, XchgDev* X) {
     X->world = ex->world;
     X->parity = (int)(ex->epoch & 1ull);
     X->defer = (ex->flags & PIL_XCHG_DEFER_FINALIZE) ? 1 : 0;
+    X->device_epoch = (ex->flags & PIL_XCHG_DEVICE_EPOCH) ? 1 : 0;
+    if (X->defer && X->device_epoch) return PIL_ERR_EXCHANGE;  // the deferred finalize kernel takes its epoch from the host
     X->want = (ex->epoch % 0xfffffffeull) + 1ull;  // 32-bit step tag, never 0 (mailboxes start zeroed)
     X->timeout_ns = xchg_timeout_ns();
     for (int r = 0; r < ex->world; ++r) {
@@ -425,7 +459,7 @@ static int backward_impl(const void* x, const void* t, void* grad, int64_t B, in
     t_info.bwd_blocks = blocks;
     t_info.bwd_threads = kThreads;
     t_info.bwd_rows_per_segment = lo.rows;
-    t_info.bwd_aligned = aligned ? 1 : 0;
+    t_info.bwd_aligned = aligned ? (lo.tma ? 2 : 1) : 0;
     count_launch();
     return (int)e;
 }
@@ -507,7 +541,7 @@ int pil_forward_pointwise(const void* x, const void* t, int64_t B, int64_t H, in
 }
 
 // ---- data-parallel training step over the peer-memory exchange (no NCCL call, 2 launches) --------
-size_t pil_exchange_bytes(void) { return (size_t)kXchgStatusOffset + 128; }
+size_t pil_exchange_bytes(void) { return (size_t)kXchgStatusOffset + 128; }  // slots, status word, device epoch counter
 
 int pil_exchange_alloc(void** mailbox, void* ipc_handle_out) {
     if (!mailbox) return PIL_ERR_NULL;
@@ -720,6 +754,11 @@ int pil_debug_bounds(unsigned long long* out4) {  // {bad reads, bad writes, fir
 #ifdef PIL_TIMELINE
 int pil_debug_timeline(void* buf) { return (int)cudaMemcpyToSymbol(pil::g_timeline, &buf, sizeof(buf)); }
 #endif
+
+int pil_set_bwd_staging(int mode) {
+    host_state().bwd_stage.store(mode < 0 ? -1 : (mode ? 1 : 0));
+    return PIL_OK;
+}
 
 int pil_set_l2_keep_mb(int mb) {
     host_state().l2_keep_mb.store(mb);

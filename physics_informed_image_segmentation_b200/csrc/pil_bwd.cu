@@ -1,8 +1,13 @@
 // pil_bwd.cu -- K2, the fused backward kernel (+ stencil sums in accumulate mode), and its launcher.
 // Compiled once per input kind (-DPIL_KIND=0|1|2); without PIL_KIND all three kinds are instantiated here.
+#include <type_traits>
+
 #include "pil_common.cuh"
 
 namespace pil {
+
+constexpr int kBwdTmaDefault = 1;  // staging of the aligned backward when nothing is forced: TMA boxes (A/B in DESIGN.md)
+
 // ------------------------------------------------------------------------------------------------
 // K2: fused backward
 // ------------------------------------------------------------------------------------------------
@@ -62,12 +67,27 @@ static __device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const double*
         }
         if (A.task_counter != nullptr) *A.task_counter = 0u;  // every warp has made its last claim
         *A.ticket = 0u;
+        if (A.X.world > 0) xchg_advance_epoch(A.X);  // device-epoch mode: this rank has completed the step
     }
 }
 
-template <int KIND, typename XT, typename TT, bool ALIGNED>
-__global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const BwdArgs A) {
+// TMA (ALIGNED only): the rows travel as 2-D tensor-map boxes (cp.async.bulk.tensor, one elected lane per warp, an
+// mbarrier per stage) instead of one 16-byte cp.async per lane per row -- see the staged paths below.
+template <int KIND, typename XT, typename TT, bool ALIGNED, bool TMA>
+__device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] const CUtensorMap* tmx, [[maybe_unused]] const CUtensorMap* tmt) {
+    static_assert(ALIGNED || !TMA, "the TMA stage ring needs the aligned layout");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    [[maybe_unused]] unsigned int tma_q = 0;  // TMA: boxes this warp has consumed so far (stage = q & 1, phase = (q >> 1) & 1)
+    if constexpr (TMA) {
+        extern __shared__ __align__(128) unsigned char smem_tma[];
+        if (threadIdx.x == 0) {
+            const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem_tma + TmaRing<XT, TT>::kBarOffset);
+#pragma unroll
+            for (int q = 0; q < 2 * kWarpsPerBlock; ++q) mbar_init(bars + 8 * q, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     const Geo& g = A.g;
     const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
     TL_STAMP(1, 0);
@@ -112,10 +132,17 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
     TL_STAMP(1, 1);
 
     // ---- global sums: given, or (data parallel) collected from the peer mailbox -----------------
+    // Every block waits here for all ranks' pointwise sums.  The rows this block starts with were already
+    // requested into L2 before pdl_wait(), so their DRAM latency overlaps the wait.  Waiting any later does not
+    // pay: the Dice term beta rides in the transposed horizontal stencil from the first residual row on, and
+    // the first gradient row leaves two rows (~1 us) after a range starts.  A wait that timed out (a peer died
+    // or is out of lock step) zeroes every coefficient: the rank writes a ZERO gradient and a NaN loss, and
+    // sets the mailbox status word, instead of poisoning the weights.
     __shared__ double s_gs[PIL_NSUMS];
     const double* gs = A.gsums;
+    bool xchg_ok = true;
     if (A.X.world > 0) {
-        xchg_wait_sum(A.X, 0, s_gs);
+        xchg_ok = xchg_wait_sum(A.X, 0, s_gs);
         gs = s_gs;
     }
 
@@ -134,10 +161,12 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         const double s = A.p.smooth, den = P + T + s;
         double scale = (double)A.grad_scale * (A.upstream ? (double)__ldg(A.upstream) : 1.0);
         if (KIND == PIL_X_LOGITS_TANH) scale *= 2.0;  // d/dz sigmoid(2z) = 2 u (1-u)
-        const double invN = 1.0 / (A.n_global > 0 ? (double)A.n_global : gs[7]);
+        if (!xchg_ok) scale = 0.0;
+        const double invN = xchg_ok ? 1.0 / (A.n_global > 0 ? (double)A.n_global : gs[7]) : 0.0;
+        const double dice_a = xchg_ok ? -2.0 / den : 0.0, dice_b = xchg_ok ? (2.0 * I + s) / (den * den) : 0.0;
         const bool use_rd = A.p.pde_weight > 0.0, use_pf = A.p.phase_field_weight > 0.0;
-        c.alpha = (float)(scale * A.p.dice_weight * (-2.0 / den));
-        c.beta = (float)(scale * A.p.dice_weight * (2.0 * I + s) / (den * den));
+        c.alpha = (float)(scale * A.p.dice_weight * dice_a);
+        c.beta = (float)(scale * A.p.dice_weight * dice_b);
         c.cb = (float)(scale * A.p.bce_weight * invN);
         const double crd = use_rd ? scale * A.p.pde_weight * 2.0 * invN : 0.0;
         c.cA = (float)(crd * A.p.diffusion_coeff);
@@ -224,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
                        float4& uc4, float4& gm4, float4& g04, float4& gp4) {
         constexpr bool CHECK = decltype(check)::value;
         uc4 = act4<KIND>(cx.fix(xn));  // row k+1
+        if (CHECK && k + 1 == H) uc4 = ua;  // row H := row H-2 (src/pde.py:67), which is row k-1
         const float va[4] = {ua.x, ua.y, ua.z, ua.w};
         const float vc[4] = {uc4.x, uc4.y, uc4.z, uc4.w};
         float gm[4] = {gm4.x, gm4.y, gm4.z, gm4.w};
@@ -341,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
                               float4& uc4, float4& gm4, float4& g04, float4& gp4) {
         constexpr bool CHECK = decltype(check)::value;
         uc4 = act4<KIND>(cx.fix(xn));  // row k+1
+        if (CHECK && k + 1 == H) uc4 = ua;  // row H := row H-2 (src/pde.py:67), which is row k-1
         const f2 va[2] = {make_float2(ua.x, ua.y), make_float2(ua.z, ua.w)};
         const f2 vc[2] = {make_float2(uc4.x, uc4.y), make_float2(uc4.z, uc4.w)};
         f2 gm[2] = {make_float2(gm4.x, gm4.y), make_float2(gm4.z, gm4.w)};
@@ -429,7 +460,86 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
         }
     };
 
-    if constexpr (ALIGNED) {
+    if constexpr (ALIGNED && TMA) {
+        // ---- TMA staged path.  Rows travel in BOXES of 6 rows x 128 columns, one box of the map and one of the
+        // targets per stage, two stages per warp.  Box n of a segment holds map rows r0+2+6n.. and target rows
+        // r0+6n.., i.e. exactly what iterations k = r0+1+6n .. r0+6+6n consume (map row k+1, target row k-1); the
+        // two head iterations (k = r0-1, r0) take map rows r0, r0+1 from direct loads issued together with the
+        // two halo rows.  One elected lane arms the stage's mbarrier with the byte count and issues the two
+        // cp.async.bulk.tensor copies; all lanes wait on the mbarrier's phase and read their 16 bytes per row
+        // with LDS.128.  Out-of-tensor parts of a box (column -4 of the first strip, columns >= W, rows past
+        // the shard) are zero-filled by the TMA unit and never used; the mirror fix-up stays at consume time.
+        using Ring = TmaRing<XT, TT>;
+        extern __shared__ __align__(128) unsigned char smem_tma[];
+        const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(smem_tma) + warp * 2 * Ring::kStageBytes;
+        const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(smem_tma) + Ring::kBarOffset + 16 * warp;
+        const int c0 = strip * kStripCols - kVec;  // first column of the warp's 128-column window
+        const int cbx = TmaBox<XT>::first_col(c0), cbt = TmaBox<TT>::first_col(c0);  // first columns of the (16-byte aligned) boxes
+        const int xoff = (cx.colc - cbx) * (int)sizeof(XT), toff = (cx.colc - cbt) * (int)sizeof(TT) + Ring::kXSlotBytes;
+        const int nb = (r1 - r0 - 1) / Ring::kBoxRows + 1;  // boxes this segment consumes
+        const int rowt = (int)((long long)b * H) + r0;         // flattened row of target box 0; map boxes start 2 rows later
+        const unsigned int q0 = tma_q;
+        auto issue_box = [&](int n) {
+            if (lane == 0) {
+                const uint32_t st = (q0 + (unsigned)n) & 1u;
+                const uint32_t dst = wbase_s + st * Ring::kStageBytes, bar = bar_s + 8 * st;
+                mbar_expect_tx(bar, Ring::kXBoxBytes + Ring::kTBoxBytes);
+                tma_load_2d(dst, tmx, cbx, rowt + 2 + Ring::kBoxRows * n, bar);
+                tma_load_2d(dst + Ring::kXSlotBytes, tmt, cbt, rowt + Ring::kBoxRows * n, bar);
+            }
+        };
+        const float4 xh0 = cx.template load<XT>(xrow(r0)), xh1 = cx.template load<XT>(xrow(r0 + 1));
+        __syncwarp();  // every lane is done with the previous segment's stages
+        issue_box(0);
+        if (nb > 1) issue_box(1);
+        U0 = act4<KIND>(cx.fix(xa));   // row k0-1
+        U1 = act4<KIND>(cx.fix(xbq));  // row k0
+        auto rotate = [&]() {
+            U0 = U1;
+            U1 = U2;
+            G0 = G1;
+            G1 = G2;
+        };
+        compute(k0, BoolC<true>{}, xh0, zero4, U0, U1, U2, G0, G1, G2);  // k = r0-1: forms r[r0-1], emits nothing
+        rotate();
+        compute(k0 + 1, BoolC<true>{}, xh1, zero4, U0, U1, U2, G0, G1, G2);  // k = r0: forms r[r0], emits nothing
+        rotate();
+        int k = r0 + 1, n = 0;
+        const int kclean = (r1 == H) ? r1 - 2 : r1 - 1;  // last iteration that needs no row / segment checks
+        // this lane's 4 columns of box row `row` of the stage at shared address sp
+        auto rd_x = [&](uint32_t sp, int row) { return lds4s<XT>(sp + xoff + row * Ring::kXRowBytes); };
+        auto rd_t = [&](uint32_t sp, int row) { return lds4s<TT>(sp + toff + row * Ring::kTRowBytes); };
+#pragma unroll 1
+        for (; k + Ring::kBoxRows - 1 <= kclean; k += Ring::kBoxRows, ++n) {
+            const unsigned int g_ = q0 + (unsigned)n;
+            mbar_wait(bar_s + 8 * (g_ & 1u), (g_ >> 1) & 1u);
+            const uint32_t sp = wbase_s + (g_ & 1u) * Ring::kStageBytes;
+            compute(k + 0, BoolC<false>{}, rd_x(sp, 0), rd_t(sp, 0), U0, U1, U2, G0, G1, G2);
+            compute(k + 1, BoolC<false>{}, rd_x(sp, 1), rd_t(sp, 1), U1, U2, U0, G1, G2, G0);
+            compute(k + 2, BoolC<false>{}, rd_x(sp, 2), rd_t(sp, 2), U2, U0, U1, G2, G0, G1);
+            compute(k + 3, BoolC<false>{}, rd_x(sp, 3), rd_t(sp, 3), U0, U1, U2, G0, G1, G2);
+            compute(k + 4, BoolC<false>{}, rd_x(sp, 4), rd_t(sp, 4), U1, U2, U0, G1, G2, G0);
+            compute(k + 5, BoolC<false>{}, rd_x(sp, 5), rd_t(sp, 5), U2, U0, U1, G2, G0, G1);
+            __syncwarp();  // all lanes have read the stage: it can be refilled
+            if (n + 2 < nb) issue_box(n + 2);
+        }
+        {
+            int row = 0;  // the tail starts on a box boundary; boxes n, n+1 are already in flight
+#pragma unroll 1
+            for (; k <= r1; ++k) {
+                const unsigned int g_ = q0 + (unsigned)n;
+                if (row == 0) mbar_wait(bar_s + 8 * (g_ & 1u), (g_ >> 1) & 1u);
+                const uint32_t sp = wbase_s + (g_ & 1u) * Ring::kStageBytes;
+                compute(k, BoolC<true>{}, rd_x(sp, row), rd_t(sp, row), U0, U1, U2, G0, G1, G2);
+                rotate();
+                if (++row == Ring::kBoxRows) {
+                    row = 0;
+                    ++n;
+                }
+            }
+        }
+        tma_q = q0 + (unsigned)nb;
+    } else if constexpr (ALIGNED) {
         // ---- staged path: iteration k consumes stage (k-k0)%6 = {map row k+1, target row k-1} ----
         extern __shared__ __align__(16) unsigned char smem_raw[];
         StageRing<XT, TT> ring;
@@ -549,6 +659,18 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const 
     bwd_epilogue(A, acc, gs);
     TL_STAMP(1, 3);
 }
+
+template <int KIND, typename XT, typename TT, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel(const BwdArgs A) {
+    bwd_body<KIND, XT, TT, ALIGNED, false>(A, nullptr, nullptr);
+}
+// same kernel with the rows staged by TMA boxes; the two tensor maps (x and t as (B*H) x W matrices) are kernel
+// parameters in constant space, where the TMA unit reads them
+template <int KIND, typename XT, typename TT>
+__global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel_tma(const BwdArgs A, const __grid_constant__ CUtensorMap tmx,
+                                                                              const __grid_constant__ CUtensorMap tmt) {
+    bwd_body<KIND, XT, TT, true, true>(A, &tmx, &tmt);
+}
 // Rows per dynamically claimed range of the backward kernel.  PIL_BWD_ROWS forces a value (0 = static
 // partition).  Automatic: 64 rows -- long enough to amortise the 4 halo rows and the pipeline fill of a
 // range, short enough to balance.  Measured on B200 at 64x1024^2 fp32: static 157.8 us; dynamic 24 rows
@@ -567,11 +689,30 @@ static int bwd_dynamic_rows(long long total_rows, long long strips, long long re
     const double waves = (double)(((total_rows + rows - 1) / rows) * strips) / (double)resident_warps;
     return waves < 2.5 ? 0 : rows;
 }
+// How the aligned backward stages its rows: 1 = TMA boxes (cp.async.bulk.tensor + mbarrier), 0 = per-lane cp.async.
+// pil_set_bwd_staging() / PIL_BWD_STAGE=tma|cpasync override the default.
+static bool bwd_want_tma() {
+    const int forced = host_state().bwd_stage.load();
+    if (forced >= 0) return forced == 1;
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("PIL_BWD_STAGE");
+        env = (e && (e[0] == 'c' || e[0] == '0')) ? 0 : ((e && (e[0] == 't' || e[0] == '1')) ? 1 : kBwdTmaDefault);
+    }
+    return env == 1;
+}
+template <typename T>
+constexpr int dtype_code() {
+    return std::is_same<T, float>::value ? PIL_F32 : (std::is_same<T, __nv_bfloat16>::value ? PIL_BF16 : PIL_U8);
+}
+
 template <int KIND, typename XT, typename TT>
 static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned, cudaStream_t s, LaunchOut* out) {
-    static std::atomic<int> per_sm_cache[2][kMaxDevices];  // per template instantiation x {scalar, aligned} kernel x device
-    auto go = [&](auto kernel, int smem) -> cudaError_t {
-        const int per_sm = blocks_per_sm_cached(kernel, kThreads, smem, per_sm_cache[aligned ? 1 : 0], true);
+    static std::atomic<int> per_sm_cache[3][kMaxDevices];  // per template instantiation x {scalar, cp.async, TMA} kernel x device
+    auto go = [&](auto kernel, int smem, int which, const auto&... extra) -> cudaError_t {
+        if (smem > 48 * 1024 && per_sm_cache[which][current_device()].load(std::memory_order_relaxed) == 0)
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const int per_sm = blocks_per_sm_cached(kernel, kThreads, smem, per_sm_cache[which], true);
         const int tune_rps = host_state().tune_bwd_rps.load();
         const int resident = sm_count() * per_sm;
         const long long strips_ = (W + kStripCols - 1) / kStripCols;
@@ -595,10 +736,20 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
             out->status = PIL_ERR_WORKSPACE;
             return cudaSuccess;
         }
-        return launch_pdl(kernel, out->blocks, kThreads, smem, s, a);
+        return launch_pdl(kernel, out->blocks, kThreads, smem, s, a, extra...);
     };
-    if (aligned) return go(pil_bwd_kernel<KIND, XT, TT, true>, kSmemPerBlock);
-    return go(pil_bwd_kernel<KIND, XT, TT, false>, 0);
+    if (aligned) {
+        using Ring = TmaRing<XT, TT>;
+        CUtensorMap tmx, tmt;
+        if (bwd_want_tma() &&
+            make_tensor_map_2d(&tmx, a.x, dtype_code<XT>(), (long long)B * H, W, Ring::kBoxRows, TmaBox<XT>::kCols) &&
+            make_tensor_map_2d(&tmt, a.t, dtype_code<TT>(), (long long)B * H, W, Ring::kBoxRows, TmaBox<TT>::kCols)) {
+            out->tma = 1;
+            return go(pil_bwd_kernel_tma<KIND, XT, TT>, Ring::kSmemBytes, 2, tmx, tmt);
+        }
+        return go(pil_bwd_kernel<KIND, XT, TT, true>, kSmemPerBlock, 1);
+    }
+    return go(pil_bwd_kernel<KIND, XT, TT, false>, 0, 0);
 }
 #define PIL_BWD_ARGS BwdArgs &a, int64_t B, int64_t H, int64_t W, bool aligned, cudaStream_t s, LaunchOut *out
 #define PIL_BWD_PASS a, B, H, W, aligned, s, out

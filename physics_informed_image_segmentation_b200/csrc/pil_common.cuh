@@ -24,6 +24,7 @@
 //     factors.
 #ifndef PIL_COMMON_CUH_
 #define PIL_COMMON_CUH_
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -240,6 +241,34 @@ __device__ __forceinline__ float4 lds4<uint8_t>(const unsigned char* p) {
                        (float)(raw >> 24));
 }
 
+// the same three readers on a 32-bit shared-space address (TMA ring: no generic-pointer arithmetic in the loop);
+// volatile keeps them behind the mbarrier wait that precedes them
+template <typename T>
+__device__ __forceinline__ float4 lds4s(uint32_t a);
+template <>
+__device__ __forceinline__ float4 lds4s<float>(uint32_t a) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+template <>
+__device__ __forceinline__ float4 lds4s<__nv_bfloat16>(uint32_t a) {
+    uint2 raw;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "r"(a));
+    float4 r;
+    r.x = __uint_as_float(raw.x << 16);
+    r.y = __uint_as_float(raw.x & 0xffff0000u);
+    r.z = __uint_as_float(raw.y << 16);
+    r.w = __uint_as_float(raw.y & 0xffff0000u);
+    return r;
+}
+template <>
+__device__ __forceinline__ float4 lds4s<uint8_t>(uint32_t a) {
+    uint32_t raw;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(a));
+    return make_float4((float)(raw & 0xff), (float)((raw >> 8) & 0xff), (float)((raw >> 16) & 0xff), (float)(raw >> 24));
+}
+
 template <typename XT, typename TT>
 struct StageRing {
     unsigned char* my;   // generic pointer to this lane's slot of stage 0 (map piece); target piece at +512
@@ -257,6 +286,57 @@ struct StageRing {
     __device__ __forceinline__ float4 read_x(int stage) const { return lds4<XT>(my + stage * kStageBytes); }
     __device__ __forceinline__ float4 read_t(int stage) const { return lds4<TT>(my + stage * kStageBytes + 512); }
 };
+
+// ------------------------------------------------------------------------------------------------
+// TMA stage ring (ALIGNED path, Blackwell-native alternative to the cp.async ring above): a warp's rows arrive
+// as 2-D tensor-map BOXES of kBoxRows rows x 128 columns -- one cp.async.bulk.tensor for the map and one for
+// the targets per box, issued by ONE elected lane and completed on an mbarrier (complete_tx::bytes) -- instead
+// of one 16-byte cp.async per lane per row per map.  Two stages per warp; the consumer waits on the stage's
+// mbarrier phase and reads with the same LDS.128 as before.  Per 6 rows this replaces 12 LDGSTS + 6 commit +
+// 6 wait + the per-row pointer arithmetic with 2 UTMALDG + 1 arrive.expect_tx + 1 try_wait.
+// ------------------------------------------------------------------------------------------------
+// The TMA unit wants the first byte of a box 16-byte aligned in the innermost dimension.  A warp's window
+// starts at column 120*strip - 4, a multiple of 4 elements: 16 bytes for fp32, but only 8 / 4 bytes for bf16 / u8
+// maps.  Those boxes start at the window's column rounded DOWN to 16 bytes and are correspondingly wider.
+template <typename T>
+struct TmaBox {
+    static constexpr int kAlign = 16 / (int)sizeof(T);                                      // elements per 16 bytes
+    static constexpr int kCols = ((32 * kVec + kAlign - kVec) + kAlign - 1) / kAlign * kAlign;  // 128 | 136 | 144
+    static constexpr int kRowBytes = kCols * (int)sizeof(T);
+    __device__ __forceinline__ static int first_col(int c0) { return c0 - (((c0 % kAlign) + kAlign) % kAlign); }
+};
+template <typename XT, typename TT>
+struct TmaRing {
+    static constexpr int kBoxRows = 6;                     // == unroll factor of the steady-state loops
+    static constexpr int kXRowBytes = TmaBox<XT>::kRowBytes, kTRowBytes = TmaBox<TT>::kRowBytes;
+    static constexpr int kXBoxBytes = kBoxRows * kXRowBytes, kTBoxBytes = kBoxRows * kTRowBytes;  // what the TMA unit delivers
+    static constexpr int kXSlotBytes = (kXBoxBytes + 127) / 128 * 128, kTSlotBytes = (kTBoxBytes + 127) / 128 * 128;
+    static constexpr int kStageBytes = kXSlotBytes + kTSlotBytes;  // every box starts 128-byte aligned
+    static constexpr int kBarOffset = kWarpsPerBlock * 2 * kStageBytes;
+    static constexpr int kSmemBytes = kBarOffset + kWarpsPerBlock * 2 * 8;
+};
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PIL_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PIL_MBAR_DONE_%=;\n"
+        "bra PIL_MBAR_WAIT_%=;\n"
+        "PIL_MBAR_DONE_%=:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// one 2-D box: tensor-map coordinates {column, row} (may be negative / past the end: zero-filled)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_shared, const CUtensorMap* map, int col, int row, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_shared),
+                 "l"(map), "r"(col), "r"(row), "r"(bar) : "memory");
+}
 
 // How one thread reads its 4 columns of a row.  ALIGNED (W % 4 == 0, 16-byte aligned bases): every
 // lane issues one 128-bit load at its column clamped into the image, so the load is branch-free;
@@ -359,10 +439,12 @@ struct Geo {
 // peer-memory exchange descriptor handed to the kernels (see the exchange helpers below)
 constexpr int kSlotBytes = 128;  // 16 words of {32-bit payload half, 32-bit step tag}
 constexpr int kXchgStatusOffset = 2 * 2 * PIL_MAX_RANKS * kSlotBytes;  // int status word after the slots
+constexpr int kXchgEpochOffset = kXchgStatusOffset + 8;                 // device-resident step counter (PIL_XCHG_DEVICE_EPOCH)
 struct XchgDev {
     int rank, world;             // world == 0: exchange disabled
     int parity;
     int defer;                   // PIL_XCHG_DEFER_FINALIZE: the backward only pushes phase 1
+    int device_epoch;            // PIL_XCHG_DEVICE_EPOCH: tag and parity come from the counter in the own mailbox
     unsigned long long want;     // flag value of this step (epoch + 1)
     unsigned long long timeout_ns;
     unsigned char* box[PIL_MAX_RANKS];
@@ -487,34 +569,62 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 constexpr int kSlotWords = 2 * PIL_NSUMS;
 static_assert(kSlotWords * 8 == kSlotBytes, "slot layout");
 
+// Step tag and slot parity.  Host epoch: both come with the descriptor.  Device epoch (PIL_XCHG_DEVICE_EPOCH):
+// they derive from a counter in the rank's OWN mailbox that the backward's last block increments when the
+// step is complete -- the kernel arguments are then identical from step to step, so the pair of launches
+// can be captured once in a CUDA graph and replayed.  Every rank counts the same completed steps.
+__device__ __forceinline__ void xchg_epoch(const XchgDev& X, unsigned long long& want, int& parity) {
+    want = X.want;
+    parity = X.parity;
+    if (X.device_epoch) {
+        unsigned long long e;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(X.box[X.rank] + kXchgEpochOffset) : "memory");
+        want = (e % 0xfffffffeull) + 1ull;
+        parity = (int)(e & 1ull);
+    }
+}
+// the step is complete on this rank: called by ONE thread of the backward's last block, after its last wait
+__device__ __forceinline__ void xchg_advance_epoch(const XchgDev& X) {
+    if (X.device_epoch) {
+        unsigned long long* p = reinterpret_cast<unsigned long long*>(X.box[X.rank] + kXchgEpochOffset);
+        *p = *p + 1ull;
+    }
+}
 // called by ALL threads of ONE block (blockDim >= 16*world): v (shared memory) -> every rank's mailbox
 __device__ __forceinline__ void xchg_push(const XchgDev& X, int phase, const double* v) {
     const int i = (int)threadIdx.x;
     if (i < kSlotWords * X.world) {
+        unsigned long long want;
+        int parity;
+        xchg_epoch(X, want, parity);
         const int r = i / kSlotWords, w = i % kSlotWords;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(v[w >> 1]);
         const unsigned long long half = (w & 1) ? (bits >> 32) : (bits & 0xffffffffull);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(xchg_slot(X.box[r], phase, X.parity, X.rank)) + w;
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(half | (X.want << 32)) : "memory");
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(xchg_slot(X.box[r], phase, parity, X.rank)) + w;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(half | (want << 32)) : "memory");
     }
 }
 // called by ALL threads of ONE block (blockDim >= 16*world; contains __syncthreads): waits for the R
 // vectors of `phase` in the LOCAL mailbox and adds them in rank order into out[0..7] (shared memory).
-// On timeout the sums are NaN and the mailbox status word is set.
-static __device__ __noinline__ void xchg_wait_sum(const XchgDev& X, int phase, double* out) {
+// On timeout the sums are NaN, the mailbox status word is set and the function returns false (block-uniform):
+// the backward then writes a ZERO gradient, so a rank that lost its peers cannot poison the weights.
+static __device__ __noinline__ bool xchg_wait_sum(const XchgDev& X, int phase, double* out) {
     __shared__ unsigned int s_half[PIL_MAX_RANKS * kSlotWords];
     __shared__ int s_bad;
     const int i = (int)threadIdx.x;
     if (i == 0) s_bad = 0;
     __syncthreads();
     if (i < kSlotWords * X.world) {
+        unsigned long long want;
+        int parity;
+        xchg_epoch(X, want, parity);
         const int r = i / kSlotWords, w = i % kSlotWords;
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(xchg_slot(X.box[X.rank], phase, X.parity, r)) + w;
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(xchg_slot(X.box[X.rank], phase, parity, r)) + w;
         const unsigned long long t0 = globaltimer_ns();
         unsigned long long word;
         for (;;) {
             asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
-            if ((word >> 32) == X.want) break;
+            if ((word >> 32) == want) break;
             if (globaltimer_ns() - t0 > X.timeout_ns) {
                 s_bad = 1;
                 break;
@@ -534,6 +644,7 @@ static __device__ __noinline__ void xchg_wait_sum(const XchgDev& X, int phase, d
     }
     if (i == 0 && s_bad) *reinterpret_cast<volatile int*>(X.box[X.rank] + kXchgStatusOffset) = 1;
     __syncthreads();
+    return s_bad == 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -666,6 +777,7 @@ struct HostState {
     std::atomic<long long> kernels_launched{0};
     std::atomic<int> tune_fwd_rps{0}, tune_bwd_rps{0};
     std::atomic<long long> l2_keep_mb{-1};  // < 0: PIL_L2_KEEP_MB or the default
+    std::atomic<int> bwd_stage{-1};         // pil_set_bwd_staging: 0 cp.async, 1 TMA, < 0 default / PIL_BWD_STAGE
 };
 HostState& host_state();  // pil_api.cu
 extern thread_local PilLaunchInfo t_info;  // how the last launch on this host thread was tiled
@@ -725,6 +837,7 @@ struct LaunchOut {
     int blocks = 0, rows = 0;
     int status = PIL_OK;              // PIL_ERR_WORKSPACE when the partials do not fit
     size_t partials_avail = ~(size_t)0;  // in: bytes of the per-block partials area (backward, accumulate mode)
+    int tma = 0;                         // out: rows staged by TMA boxes
 };
 // Rows per range the kernels like best (measured on B200, 64x1024^2 .. 128x2048^2): long enough to
 // amortise the warm-up rows and the pipeline fill of a segment, short enough that the hardware block
@@ -755,8 +868,8 @@ inline bool use_pdl() {
     }
     return v == 1;
 }
-template <typename K, typename A>
-inline cudaError_t launch_pdl(K kernel, int blocks, int threads, int smem, cudaStream_t s, const A& args) {
+template <typename K, typename... A>
+inline cudaError_t launch_pdl(K kernel, int blocks, int threads, int smem, cudaStream_t s, const A&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)blocks);
     cfg.blockDim = dim3((unsigned)threads);
@@ -767,8 +880,12 @@ inline cudaError_t launch_pdl(K kernel, int blocks, int threads, int smem, cudaS
     at[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, args);
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+
+// 2-D tensor map of a (rows x cols) row-major map with a (box_rows x box_cols) box; false when the layout does not
+// qualify (TMA needs a 16-byte aligned base and row pitch) or the driver entry point is unavailable.  pil_api.cu
+bool make_tensor_map_2d(CUtensorMap* out, const void* base, int dtype, long long rows, long long cols, int box_rows, int box_cols);
 
 // per-kind launchers, one translation unit each in release builds (pil_fwd.cu, pil_point.cu, pil_bwd.cu)
 #define PIL_DECL_KIND(K)                                                                                                        \
