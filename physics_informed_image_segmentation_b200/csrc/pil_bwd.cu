@@ -24,6 +24,11 @@ struct BwdCoef {
     float beta_half;     // beta / 2 (travels with the horizontal transposed-stencil terms)
     float f1c;           // f1 - 4 cA  (centre tap of the transposed Laplacian folded into f')
     float cW2n;          // -2 cW       (cW uv (1-2u) = uv (cW2n u + cW))
+    // packed path works on rho = r / D = (sum of 4 neighbours) + u*(u*(a1/D - u/D) + c0/D): one multiply less per
+    // pixel; every coefficient that meets r carries the factor D instead, and sum r^2 = D^2 sum rho^2
+    float nDi, a1D, c0D;  // -1/D, a1/D, c0/D
+    float cAD;            // cA * D
+    float f3D, f2D, f1cD; // (cF f'(u) - 4 cA) * D as a polynomial in u
 };
 
 // accumulate mode: reduce the stencil sums across the grid; the last block publishes them and,
@@ -181,6 +186,14 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
         c.beta_half = 0.5f * c.beta;
         c.f1c = (float)(-A.p.reaction_threshold * crd - 4.0 * crd * A.p.diffusion_coeff);
         c.cW2n = -2.0f * c.cW;
+        const double Dd = A.p.diffusion_coeff;
+        c.nDi = (float)(-1.0 / Dd);
+        c.a1D = (float)((1.0 + A.p.reaction_threshold) / Dd);
+        c.c0D = (float)((-A.p.reaction_threshold - 4.0 * Dd) / Dd);
+        c.cAD = (float)(crd * Dd * Dd);
+        c.f3D = (float)(-3.0 * crd * Dd);
+        c.f2D = (float)(2.0 * (1.0 + A.p.reaction_threshold) * crd * Dd);
+        c.f1cD = (float)((-A.p.reaction_threshold * crd - 4.0 * crd * Dd) * Dd);
     }
 
     // ---- task loop.  Equal static row ranges finish far apart (measured: 83..145 us per block at
@@ -215,7 +228,7 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
         fc[p] = in ? ((cc == 0 || cc == W - 1) ? 2.0f : 1.0f) : 0.0f;
     }
     // packed path: the same factors folded into per-slot coefficient pairs
-    const f2 cAf2[2] = {make_float2(c.cA * fc[0], c.cA * fc[1]), make_float2(c.cA * fc[2], c.cA * fc[3])};
+    const f2 cAf2[2] = {make_float2(c.cAD * fc[0], c.cAD * fc[1]), make_float2(c.cAD * fc[2], c.cAD * fc[3])};  // meet rho = r / D
     const f2 cGm2[2] = {make_float2(c.cG * mc[0], c.cG * mc[1]), make_float2(c.cG * mc[2], c.cG * mc[3])};
     const bool store_vec = ALIGNED && out_lane && in_img;
     // stencil sums of the rows this warp owns (accumulate mode): sum r^2 and sum dx^2+dy^2
@@ -388,8 +401,8 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const f2 s4 = add2(hs[h], add2(va[h], vc[h]));
-                // r = D*(s4 - 4u) + u(1-u)(u-a), as a polynomial in u   (src/pde.py:73-77,:99,:120)
-                r[h] = fma2(u[h], fma2(u[h], sub2(bc(c.a1), u[h]), bc(c.c0)), mul2(bc(c.D), s4));
+                // rho = r / D with r = D*(s4 - 4u) + u(1-u)(u-a) as a polynomial in u   (src/pde.py:73-77,:99,:120)
+                r[h] = fma2(u[h], fma2(u[h], fma2(bc(c.nDi), u[h], bc(c.a1D)), bc(c.c0D)), s4);
                 dy[h] = sub2(vc[h], va[h]);
             }
             if (!CHECK || (k >= r0 && k < r1)) {  // rows this segment owns: loss terms the light forward skipped
@@ -401,7 +414,7 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
                 }
             }
             // row factor of the transposed vertical stencil; dy of an edge row is 0 by mirroring
-            const float cAr = (CHECK && (k == 0 || k == H - 1)) ? 2.0f * c.cA : c.cA;
+            const float cAr = (CHECK && (k == 0 || k == H - 1)) ? 2.0f * c.cAD : c.cAD;
             f2 Ah[2], Bh[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -417,7 +430,7 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
             const f2 hg[2] = {make_float2(AL + Bh[0].y, Ah[0].x + Bh[1].x), make_float2(Ah[0].y + Bh[1].y, Ah[1].x + BR)};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const f2 fpr = fma2(u[h], fma2(bc(c.f3), u[h], bc(c.f2)), bc(c.f1c));  // cF f'(u) - 4 cA
+                const f2 fpr = fma2(u[h], fma2(bc(c.f3D), u[h], bc(c.f2D)), bc(c.f1cD));  // (cF f'(u) - 4 cA) * D
                 g0[h] = fma2(fpr, r[h], add2(g0[h], hg[h]));
             }
         } else {
@@ -433,8 +446,7 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const f2 u = va[h], t = vt[h];
-                const f2 v = sub2(bc(1.0f), u);
-                const f2 uv = mul2(u, v);
+                const f2 uv = fma2(make_float2(-u.x, -u.y), u, u);  // u(1-u) = u - u^2, rounded once
                 // du = gm + alpha t + cW uv (1-2u)
                 const f2 du = fma2(uv, fma2(bc(c.cW2n), u, bc(c.cW)), fma2(bc(c.alpha), t, gm[h]));
                 const f2 w = mul2(bc(c.cb), sub2(u, t));
@@ -634,7 +646,7 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
 
     if constexpr (ALIGNED) {
         if (store_vec) {
-            tot_r2 += (double)(sr2.x + sr2.y);
+            tot_r2 += (double)(sr2.x + sr2.y) * (A.p.diffusion_coeff * A.p.diffusion_coeff);  // sum r^2 = D^2 sum rho^2
             tot_g2 += (double)(sg2.x + sg2.y);
         }
     } else {
