@@ -267,6 +267,10 @@ int pil_backward_accumulate_xchg(const void* x, const void* t, void* grad, int64
                                  const PilExchange* ex, int64_t n_global, const float* upstream, float grad_scale,
                                  double* stencil_sums, float* loss_out, double* total_sums,
                                  void* workspace, size_t workspace_bytes, void* stream);
+/* Push a sums vector (device, PIL_NSUMS doubles) of this rank into every rank's mailbox, as the last block of
+ * pil_forward_pointwise_xchg does: for callers that assemble the shard's pointwise sums (phase 0) from several
+ * launches, e.g. chunk by chunk while the maps are still arriving from the host (pil_session_run_xchg). */
+int pil_exchange_push(const PilExchange* ex, int phase, const double* sums, void* stream);
 /* With PIL_XCHG_DEFER_FINALIZE the backward kernel does not wait for the other ranks' stencil sums;
  * this one-thread kernel does, later on the stream (e.g. after the optimizer step was enqueued).
  * It is also how several ranks are emulated on ONE GPU in the tests: there a kernel must never wait
@@ -307,6 +311,15 @@ int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void*
 #define PIL_SESSION_GRAD_ON_DEVICE 1
 int pil_session_run_ex(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B,
                        int x_kind, const PilParams* p, float* loss_out_host, int flags);
+/* Data-parallel form (one process per GPU, one session per rank): x_host / t_host hold THIS rank's B images of
+ * the global batch.  H2D in chunks overlapped with the pointwise forward, push of the shard's sums to every rank
+ * (pil_exchange_push), then ONE backward over the shard fed from the mailbox (pil_backward_accumulate_xchg): the
+ * gradient of the GLOBAL loss w.r.t. this rank's maps stays on the device (pil_session_grad_ptr), and
+ * loss_out_host receives the GLOBAL loss report, identical on every rank.  n_global: pixels of the global batch
+ * (<= 0: taken from the exchanged sums); grad_scale: world size under DDP-style gradient averaging. */
+int pil_session_run_xchg(PilSession* s, const void* x_host, const void* t_host, int64_t B, int x_kind,
+                         const PilParams* p, const struct PilExchange* ex, int64_t n_global, float grad_scale,
+                         float* loss_out_host);
 void* pil_session_grad_ptr(PilSession* s);
 int pil_session_destroy(PilSession* s);
 

@@ -200,6 +200,10 @@ _SIGS = {
                                        ctypes.c_int64, ctypes.c_int, ctypes.POINTER(PilParams), ctypes.c_void_p]),
     "pil_session_run_ex": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int64, ctypes.c_int, ctypes.POINTER(PilParams), ctypes.c_void_p, ctypes.c_int]),
+    "pil_session_run_xchg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                            ctypes.POINTER(PilParams), ctypes.POINTER(PilExchange), ctypes.c_int64, ctypes.c_float,
+                                            ctypes.c_void_p]),
+    "pil_exchange_push": (ctypes.c_int, [ctypes.POINTER(PilExchange), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "pil_session_grad_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "pil_session_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pil_last_launch_info": (ctypes.c_int, [ctypes.POINTER(PilLaunchInfo)]),

@@ -48,6 +48,15 @@ __global__ void pil_sweep_finalize_kernel(const double* mo, long long n_global, 
     finalize_device(s, n_global > 0 ? (double)n_global : s[7], p, out + (size_t)k * PIL_NOUT);
 }
 
+// stand-alone push of a sums vector into every rank's mailbox (pil_exchange_push): for callers that assemble the
+// shard's pointwise sums from several launches (the host-buffer session adds per-chunk sums first)
+__global__ void __launch_bounds__(kThreads) pil_xchg_push_kernel(XchgDev X, int phase, const double* sums) {
+    __shared__ double s_v[PIL_NSUMS];
+    if (threadIdx.x < PIL_NSUMS) s_v[threadIdx.x] = sums[threadIdx.x];
+    __syncthreads();
+    xchg_push(X, phase, s_v);
+}
+
 // deferred finalisation of a data-parallel step: both exchanged vectors -> the global loss report
 __global__ void __launch_bounds__(kThreads) pil_xchg_finalize_kernel(XchgDev X, long long n_global, PilParams p, float* out, double* total_sums) {
     __shared__ double s_a[PIL_NSUMS], s_b[PIL_NSUMS];
@@ -209,6 +218,8 @@ bool make_tensor_map_2d(CUtensorMap* out, const void* base, int dtype, long long
     return fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+constexpr long long kL2ResidentMB = 110;  // maps + gradient up to this size are left L2-resident by the forward (L2: 126 MB)
 
 static unsigned long long xchg_timeout_ns() {
     static unsigned long long v = 0;
@@ -508,6 +519,16 @@ static int pointwise_impl(const void* x, const void* t, int64_t B, int64_t H, in
         }
         const long long keep4 = (keep_mb << 20) / 16;  // float4s of EACH map to keep
         a.keep_from4 = (keep_mb > 0 && (a.n >> 2) > 2 * keep4) ? (a.n >> 2) - keep4 : (a.n >> 2);
+        // Small shards (a data-parallel rank of a strong-scaled batch, the reference's own 8x128x128 batches): when
+        // both maps and the gradient fit in the 126 MB L2 the stream is not "read once" at all -- the backward finds
+        // x and t in L2 if this kernel does not mark them evict_first.  Plain loads then.
+        static long long resident_mb = -1;
+        if (resident_mb < 0) {
+            const char* e = getenv("PIL_L2_RESIDENT_MB");
+            resident_mb = e ? atoll(e) : kL2ResidentMB;
+        }
+        const long long footprint = a.n * (long long)(2 * dtype_size(x_dtype) + dtype_size(t_dtype));
+        if (footprint <= (resident_mb << 20)) a.keep_from4 = (a.n >> 2);
     }
     a.ticket = reinterpret_cast<unsigned int*>((char*)workspace + wl.ticket_off);
     a.partials = reinterpret_cast<double*>((char*)workspace + wl.partials_off);
@@ -624,7 +645,8 @@ int pil_forward_pointwise_metrics(const void* x, const void* t, int64_t B, int64
     a.p = *p;
     a.image_counts = image_counts;
     a.threshold = threshold;
-    a.l2_stream = host_state().l2_keep_mb.load() != 0 ? 1 : 0;
+    a.l2_stream = (host_state().l2_keep_mb.load() != 0 &&
+                   a.n * (long long)(2 * dtype_size(x_dtype) + dtype_size(t_dtype)) > ((long long)kL2ResidentMB << 20)) ? 1 : 0;
     st = make_xchg(ex, &a.X);
     if (st != PIL_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
@@ -662,6 +684,17 @@ int pil_exchange_finalize(const PilExchange* ex, int64_t n_global, const PilPara
     int st = make_xchg(ex, &X);
     if (st != PIL_OK) return st;
     pil_xchg_finalize_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(X, (long long)n_global, *p, loss_out, total_sums);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int pil_exchange_push(const PilExchange* ex, int phase, const double* sums, void* stream) {
+    if (!ex || !sums) return PIL_ERR_NULL;
+    if (phase != 0 && phase != 1) return PIL_ERR_EXCHANGE;
+    XchgDev X;
+    int st = make_xchg(ex, &X);
+    if (st != PIL_OK) return st;
+    pil_xchg_push_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(X, phase, sums);
     count_launch();
     return (int)cudaGetLastError();
 }

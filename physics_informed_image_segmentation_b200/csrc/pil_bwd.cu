@@ -33,9 +33,12 @@ struct BwdCoef {
 
 // accumulate mode: reduce the stencil sums across the grid; the last block publishes them and,
 // if asked, assembles the loss from (global pointwise sums + these) -- src/loss.py:144-160.
-static __device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const double* acc, const double* gs) {
-    double raw[PIL_NSUMS];
-    if (!reduce_to_last_block<kThreads, double>(acc, A.partials, A.ticket, raw)) return;
+// acc2 = {sum r^2, sum dx^2+dy^2} of this thread: the only two sums the backward produces, so the cross-block
+// reduction moves 16 bytes per block instead of 64 (it is serial time at the very end of the kernel).
+static __device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const double* acc2, const double* gs) {
+    double raw2[2];
+    if (!reduce_to_last_block<kThreads, double, 2>(acc2, A.partials, A.ticket, raw2)) return;
+    const double raw[PIL_NSUMS] = {0.0, 0.0, 0.0, 0.0, raw2[0], raw2[1], 0.0, 0.0};
     __shared__ double s_push[PIL_NSUMS];   // this shard's stencil sums
     __shared__ double s_glob[PIL_NSUMS];   // the global stencil sums
     if (threadIdx.x == 0) {
@@ -153,7 +156,7 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
 
     if (task >= g.tasks) {
         if (A.accumulate) {  // idle warp of the last block still takes part in the block reduction
-            const double zero[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            const double zero[2] = {0.0, 0.0};
             bwd_epilogue(A, zero, gs);
         }
         return;
@@ -665,9 +668,7 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
 
     TL_STAMP(1, 2);
     if (!A.accumulate) return;  // uniform: plain pil_backward
-    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    acc[4] = tot_r2;
-    acc[5] = tot_g2;
+    const double acc[2] = {tot_r2, tot_g2};
     bwd_epilogue(A, acc, gs);
     TL_STAMP(1, 3);
 }
@@ -744,7 +745,7 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
             out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
         }
         out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
-        if (a.accumulate && (size_t)out->blocks * PIL_NSUMS * sizeof(double) > out->partials_avail) {
+        if (a.accumulate && (size_t)out->blocks * 2 * sizeof(double) > out->partials_avail) {
             out->status = PIL_ERR_WORKSPACE;
             return cudaSuccess;
         }

@@ -659,7 +659,7 @@ template <int THREADS, typename AccT, int N = PIL_NSUMS>
 __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* partials, unsigned int* ticket, double* out) {
     constexpr int kWarps = THREADS / 32;
     constexpr int NP = N / 2;  // component pairs (16-byte loads)
-    static_assert(N % 2 == 0 && THREADS % NP == 0, "component layout");
+    static_assert(N % 2 == 0 && THREADS % NP == 0 && (NP & (NP - 1)) == 0 && NP <= 32 && 32 % NP == 0, "component layout");
     __shared__ double s_part[kWarps][N];
     __shared__ double s_red[2 * THREADS];
     __shared__ double s_tot[N];
@@ -710,13 +710,23 @@ __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* pa
                 vy += w[q].y;
             }
         }
-        s_red[2 * threadIdx.x] = vx;       // s_red viewed as [kGroups][N]
-        s_red[2 * threadIdx.x + 1] = vy;
+        // threads with the same lane % NP hold partial sums of the same component pair: butterfly over the other
+        // lane bits (fixed pattern -> bit-reproducible), then one value per warp and pair through shared memory
+#pragma unroll
+        for (int o = 16; o >= NP; o >>= 1) {
+            vx += __shfl_xor_sync(0xffffffffu, vx, o);
+            vy += __shfl_xor_sync(0xffffffffu, vy, o);
+        }
+        if (lane < NP) {
+            s_red[(warp * NP + lane) * 2] = vx;  // s_red viewed as [kWarps][N]
+            s_red[(warp * NP + lane) * 2 + 1] = vy;
+        }
     }
     __syncthreads();
     if (threadIdx.x < N) {
         double v = 0.0;
-        for (int j = 0; j < kGroups; ++j) v += s_red[j * N + threadIdx.x];
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += s_red[w * N + threadIdx.x];
         s_tot[threadIdx.x] = v;
     }
     __syncthreads();

@@ -132,7 +132,8 @@ int pil_session_create(PilSession** out, int device, int64_t max_B, int64_t H, i
 // overlaps the H2D of chunk c+1, then ONE backward over the whole batch accumulates the stencil sums and
 // finalises the loss.
 static int session_run_impl(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B, int x_kind,
-                            const PilParams* p, float* loss_out_host, int flags) {
+                            const PilParams* p, float* loss_out_host, int flags, const PilExchange* ex = nullptr,
+                            int64_t n_global_in = 0, float grad_scale = 1.0f) {
     if (!s || !x_host || !t_host || !p || !loss_out_host) return PIL_ERR_NULL;
     if (B < 1 || B > s->max_B) return PIL_ERR_SESSION;
     int st = pil_validate_params(p);
@@ -144,7 +145,7 @@ static int session_run_impl(PilSession* s, const void* x_host, const void* t_hos
     const int chunks = (int)(B < kMaxChunks ? B : kMaxChunks);
     const int64_t n_global = B * img;
     auto first = [&](int c) { return (B * c) / chunks; };
-    const bool device_grad = (flags & PIL_SESSION_GRAD_ON_DEVICE) != 0 && grad_host == nullptr;
+    const bool device_grad = ((flags & PIL_SESSION_GRAD_ON_DEVICE) != 0 && grad_host == nullptr) || ex != nullptr;
 
     // phase 1: H2D + forward per chunk
     for (int c = 0; c < chunks; ++c) {
@@ -168,6 +169,19 @@ static int session_run_impl(PilSession* s, const void* x_host, const void* t_hos
     double* gs = s->dsums + (size_t)kMaxChunks * PIL_NSUMS;
     pil_add_chunk_sums<<<1, 32, 0, s->s_comp>>>(s->dsums, chunks, gs);
     PIL_TRY(cudaGetLastError());
+    if (ex != nullptr) {
+        // data parallel: hand the shard's pointwise sums to every rank, then one backward fed from the mailbox; its last
+        // block swaps the stencil sums and assembles the GLOBAL loss report
+        st = pil_exchange_push(ex, 0, gs, s->s_comp);
+        if (st != PIL_OK) return st;
+        st = pil_backward_accumulate_xchg(s->dx, s->dt, s->dg, B, s->H, s->W, s->x_dtype, s->t_dtype, x_kind, p, ex, n_global_in,
+                                          nullptr, grad_scale, s->dsums, s->dout, nullptr, s->ws[0], s->ws_bytes, s->s_comp);
+        if (st != PIL_OK) return st;
+        PIL_TRY(cudaMemcpyAsync(s->hout, s->dout, sizeof(float) * PIL_NOUT, cudaMemcpyDeviceToHost, s->s_comp));
+        PIL_TRY(cudaStreamSynchronize(s->s_comp));
+        for (int k = 0; k < PIL_NOUT; ++k) loss_out_host[k] = s->hout[k];
+        return PIL_OK;
+    }
     if (device_grad) {
         // one backward over the whole batch: gradient stays on the device, stencil sums + loss in the same kernel
         st = pil_backward_accumulate(s->dx, s->dt, s->dg, B, s->H, s->W, s->x_dtype, s->t_dtype, x_kind, p, gs, n_global,
@@ -212,6 +226,13 @@ int pil_session_run(PilSession* s, const void* x_host, const void* t_host, void*
 int pil_session_run_ex(PilSession* s, const void* x_host, const void* t_host, void* grad_host, int64_t B, int x_kind,
                        const PilParams* p, float* loss_out_host, int flags) {
     return session_run_impl(s, x_host, t_host, grad_host, B, x_kind, p, loss_out_host, flags);
+}
+
+int pil_session_run_xchg(PilSession* s, const void* x_host, const void* t_host, int64_t B, int x_kind, const PilParams* p,
+                         const PilExchange* ex, int64_t n_global, float grad_scale, float* loss_out_host) {
+    if (!ex) return PIL_ERR_NULL;
+    return session_run_impl(s, x_host, t_host, nullptr, B, x_kind, p, loss_out_host, PIL_SESSION_GRAD_ON_DEVICE, ex, n_global,
+                            grad_scale);
 }
 
 void* pil_session_grad_ptr(PilSession* s) { return s ? s->dg : nullptr; }

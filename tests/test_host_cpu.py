@@ -268,3 +268,37 @@ def test_header_is_plain_c(tmp_path):
     res = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c",
                           os.path.join(ROOT, "tests", "abi_check.c"), "-o", str(out)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_host_session_rejects_buffers_the_library_would_misread():
+    """The host-buffer entry takes raw pointers: non-contiguous arrays (a temporary copy would dangle, or swallow
+    the gradient), mismatched shapes / dtypes and read-only gradient buffers must be refused BEFORE the C call."""
+    from physics_informed_image_segmentation_b200 import session as S
+
+    shape = (4, 16, 24)
+    x = np.zeros((4, 1, 16, 24), np.float32)
+    t = np.zeros((4, 1, 16, 24), np.float32)
+    assert S._check_buffers(x, t, np.zeros_like(x), shape, _lib.F32, _lib.F32) == 4
+    assert S._check_buffers(x[:2], t[:2], None, shape, _lib.F32, _lib.F32) == 2
+    with pytest.raises(ValueError):
+        S._check_buffers(x, t[:3], None, shape, _lib.F32, _lib.F32)                   # smaller target buffer
+    with pytest.raises(ValueError):
+        S._check_buffers(x, t, np.zeros((4, 1, 16, 23), np.float32), shape, _lib.F32, _lib.F32)  # gradient shape
+    with pytest.raises(TypeError):
+        S._check_buffers(x, t, np.zeros(x.shape, np.float64), shape, _lib.F32, _lib.F32)         # gradient dtype
+    with pytest.raises(TypeError):
+        S._check_buffers(x.astype(np.float64), t, None, shape, _lib.F32, _lib.F32)
+    with pytest.raises(ValueError):
+        S._check_buffers(np.zeros((5, 1, 16, 24), np.float32), np.zeros((5, 1, 16, 24), np.float32), None, shape, _lib.F32, _lib.F32)
+    ro = np.zeros_like(x)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        S._check_buffers(x, t, ro, shape, _lib.F32, _lib.F32)
+    big = np.zeros((4, 1, 16, 48), np.float32)
+    with pytest.raises(ValueError):
+        S._host_ptr(big[..., ::2], "maps")                                              # strided view: never copied silently
+    with pytest.raises(ValueError):
+        S._host_ptr(torch.zeros(4, 1, 16, 48)[..., ::2], "maps")
+    with pytest.raises(TypeError):
+        S._host_ptr([[1.0, 2.0]], "maps")
+    assert S._host_ptr(x, "maps") == x.ctypes.data

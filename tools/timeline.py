@@ -1,8 +1,8 @@
 """Per-block timeline of the two hot kernels (development tool; needs a -DPIL_TIMELINE build):
 
-    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared -DPIL_TIMELINE -DPIL_DEV_F32_ONLY \
-         -I include -o build/libpil_tl.so physics_informed_image_segmentation_b200/csrc/*.cu
-    PIL_LIB=build/libpil_tl.so python tools/timeline.py [--workload cfg3] [--steps 4]
+    cd physics_informed_image_segmentation_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC \
+         -shared -DPIL_TIMELINE -DPIL_DEV_F32_ONLY -I ../../include -I . -o dev/libpil_tl.so pil_unity.cu pil_session.cu
+    PIL_LIB=physics_informed_image_segmentation_b200/csrc/dev/libpil_tl.so python tools/timeline.py [--workload cfg3 | --shape BxHxW] [--steps 4]
 
 Every block stamps %globaltimer at entry, after the PDL wait, at the end of its main loop and at exit.
 Prints, per kernel of the LAST step: start spread, loop-end spread, tail, and the gap/overlap between
@@ -24,8 +24,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg3")
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--side-stream", action="store_true")
+ap.add_argument("--shape", default="", help="BxHxW instead of a named workload")
 a = ap.parse_args()
 B, H, W, name = bench.WORKLOADS[a.workload]
+if a.shape:
+    B, H, W = (int(v) for v in a.shape.split("x"))
+    name = a.shape
 dev = torch.device("cuda:0")
 L = _lib.lib()
 L.pil_debug_timeline.restype = ctypes.c_int
