@@ -196,6 +196,28 @@ int pil_image_metrics(const double* image_counts, int64_t B, double smooth,
                       float* dice_out, float* iou_out, void* stream);
 
 /*
+ * Boundary-F1 of the thresholded prediction against the mask, per image, on the device: what
+ * compute_boundary_f1_batch (src/evaluate.py:196-229 -> compute_boundary_f1 :125-193 -> extract_boundaries :102-122)
+ * computes on the host with OpenCV for every image of every training / validation step (src/train.py:156, :259).
+ *   boundary(M)  = cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_NONE) drawn with thickness 1: the foreground pixels
+ *                  4-adjacent to background that is 4-connected to the image frame (holes contribute nothing);
+ *   within tol   = cv2.distanceTransform(DIST_L2, mask 5) <= tol: a boundary pixel of the other map at a 5x5-chamfer
+ *                  distance <= tol (tol = 2: 13 offsets); tol = 0 is the reference's exact-match branch.
+ * pil_boundary_counts leaves four integers per image (device, B x 4 int64, zeroed by the call):
+ *   [b][0] |Bp|  [b][1] |Bt|  [b][2] #{p in Bp within tol of Bt} (tol 0: |Bp & Bt|)  [b][3] #{q in Bt within tol of Bp}
+ * pil_boundary_f1 turns them into the reference's float32 F1 per image.  x: probabilities or logits (x_kind), the
+ * prediction mask is activation(x) > threshold; the target mask is (uint8)(t * 255) != 0 as in extract_boundaries.
+ * 0 <= tolerance <= 6 (the chamfer weights make larger tolerances ambiguous at equality).  Shapes: H, W >= 1.
+ * pil_boundary_tolerance_offsets lists the offsets of a tolerance (host; NULL outputs: just the count).
+ */
+size_t pil_boundary_workspace_bytes(int64_t B, int64_t H, int64_t W);
+int pil_boundary_tolerance_offsets(int tolerance, int8_t* dy_out, int8_t* dx_out, int capacity);
+int pil_boundary_counts(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,
+                        float threshold, int tolerance, long long* counts, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int pil_boundary_f1(const long long* counts, int64_t B, int tolerance, double smooth, float* f1_out, void* stream);
+
+/*
  * Parameter sweeps (BASELINE config 4; the S2/S3 sensitivity grids of run_ablation.py:159-224 evaluated as
  * ONE batched loss evaluation).  lap(u), g = u(1-u), h = g*u, |grad u|^2 and the Dice/BCE sums do not
  * depend on D, a, eps or the weights, and r = D*lap + h - a*g, so the loss for ANY setting of the knobs is a
@@ -277,6 +299,27 @@ int pil_exchange_push(const PilExchange* ex, int phase, const double* sums, void
  * for a flag that a LATER launch writes, so all backwards are enqueued first, then the finalizes. */
 int pil_exchange_finalize(const PilExchange* ex, int64_t n_global, const PilParams* p,
                           float* loss_out, double* total_sums, void* stream);
+
+/*
+ * One training-step evaluation as ONE CUDA-graph launch.  For small maps -- the reference's real batches are
+ * 8 x 1 x 128 x 128 (src/dataset.py:18), and a strong-scaled data-parallel batch leaves each GPU a small shard --
+ * a step costs what the host spends on two C-ABI calls and two launches, not what the kernels take.
+ * pil_step_graph_create runs the step once on `stream` (a real step; data parallel: on every rank, creation is
+ * collective), then captures pil_forward_pointwise[_xchg] -> pil_backward_accumulate[_xchg] with their
+ * programmatic-dependent-launch edge; pil_step_graph_launch replays the pair on any stream of the same device.
+ * The graph is BOUND to the buffers it was created with (x, t, grad, sums, loss_out, stencil_sums, workspace,
+ * upstream, total_sums): refill x / t in place between steps.  ex (may be NULL) must carry
+ * PIL_XCHG_DEVICE_EPOCH; its mailbox pointers must stay mapped while the graph lives.  total_sums: the complete
+ * sums vector (single shard: may alias sums; data parallel: the GLOBAL sums; may be NULL).
+ */
+typedef struct PilStepGraph PilStepGraph;
+int pil_step_graph_create(PilStepGraph** out, const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W,
+                          int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                          double* sums, float* loss_out, double* stencil_sums, void* workspace, size_t workspace_bytes,
+                          const struct PilExchange* ex, int64_t n_global, const float* upstream, float grad_scale,
+                          double* total_sums, void* stream);
+int pil_step_graph_launch(PilStepGraph* g, void* stream);
+int pil_step_graph_destroy(PilStepGraph* g);
 
 /*
  * The PDERegularization operators a caller can use on their own (fp32 maps):

@@ -10,7 +10,8 @@ from .functional import LossParams
 from .sharding import shard_bounds, all_reduce_sums, loss_report_from_sums
 from .session import HostSession
 from .sweep import sweep_losses, s2_grid, s3_grid
-from .metrics import compute_dice_score, compute_dice_score_batch, compute_iou, compute_iou_batch
+from .metrics import (compute_dice_score, compute_dice_score_batch, compute_iou, compute_iou_batch, compute_boundary_f1,
+                      compute_boundary_f1_batch)
 from .integration import install_into_reference, use_logits_head
 
 __all__ = [
@@ -18,5 +19,6 @@ __all__ = [
     "shard_bounds", "all_reduce_sums", "loss_report_from_sums", "HostSession",
     "install_into_reference", "use_logits_head", "sweep_losses", "s2_grid", "s3_grid",
     "compute_dice_score", "compute_dice_score_batch", "compute_iou", "compute_iou_batch",
+    "compute_boundary_f1", "compute_boundary_f1_batch",
 ]
 __version__ = "0.1.0"

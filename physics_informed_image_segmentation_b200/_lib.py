@@ -20,7 +20,7 @@ HEADERS = [os.path.join(INCLUDE, "pil.h"), os.path.join(CSRC, "pil_common.cuh"),
 # Translation units of libpil.so: (source, extra defines, object name).  The fused kernels are compiled once per
 # input kind (-DPIL_KIND) so that their template instantiations build in parallel.
 _KIND_SOURCES = ("pil_fwd.cu", "pil_point.cu", "pil_bwd.cu")
-_PLAIN_SOURCES = ("pil_api.cu", "pil_session.cu", "pil_tail.cu", "pil_boundary.cu")
+_PLAIN_SOURCES = ("pil_api.cu", "pil_session.cu", "pil_graph.cu", "pil_tail.cu", "pil_boundary.cu")
 
 
 def _units():
@@ -206,6 +206,20 @@ _SIGS = {
     "pil_exchange_push": (ctypes.c_int, [ctypes.POINTER(PilExchange), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "pil_session_grad_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "pil_session_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pil_step_graph_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.POINTER(PilParams), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(PilExchange), ctypes.c_int64,
+                                             ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "pil_step_graph_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pil_step_graph_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pil_boundary_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64] * 3),
+    "pil_boundary_tolerance_offsets": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "pil_boundary_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "pil_boundary_f1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
     "pil_last_launch_info": (ctypes.c_int, [ctypes.POINTER(PilLaunchInfo)]),
     "pil_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "pil_set_l2_keep_mb": (ctypes.c_int, [ctypes.c_int]),

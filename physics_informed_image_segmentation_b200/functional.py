@@ -332,6 +332,49 @@ def image_metrics(counts: torch.Tensor, smooth: float = 1e-6) -> Tuple[torch.Ten
     return dice, iou
 
 
+_BOUNDARY_WS = {}
+
+
+def boundary_counts(x: torch.Tensor, t: torch.Tensor, kind: int = X_PROB, threshold: float = 0.5, tolerance: int = 2,
+                    counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-image boundary counts (int64[B, 4]: |Bp|, |Bt|, #Bp within tolerance of Bt, #Bt within tolerance of Bp) of
+    the thresholded prediction against the mask -- the integers behind the reference's OpenCV boundary-F1
+    (src/evaluate.py:102-193), counted on the device without a host sync (include/pil.h pil_boundary_counts)."""
+    if not x.is_cuda:
+        raise RuntimeError("CUDA tensors only (no CPU fallback)")
+    if t.shape != x.shape or t.device != x.device or not x.is_contiguous() or not t.is_contiguous():
+        raise RuntimeError("predictions and targets must be contiguous tensors of one shape on one device")
+    if not (0 <= int(tolerance) <= 6):
+        raise NotImplementedError("boundary tolerance must be an integer in [0, 6]")
+    B, H, W = _bhw(x)
+    dev = x.device
+    if counts is None:
+        counts = torch.empty(B, 4, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    need = L.pil_boundary_workspace_bytes(B, H, W)
+    key = (dev.index, _stream_ptr(dev))
+    ws = _BOUNDARY_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _BOUNDARY_WS[key] = ws
+    with torch.cuda.device(dev):
+        st = L.pil_boundary_counts(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind, float(threshold),
+                                   int(tolerance), counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(st, "pil_boundary_counts")
+    return counts
+
+
+def boundary_f1(counts: torch.Tensor, tolerance: int = 2, smooth: float = 1e-6) -> torch.Tensor:
+    """float32[B] boundary-F1 from the counts, with the reference's float32 arithmetic (src/evaluate.py:171-191)."""
+    B = counts.shape[0]
+    dev = counts.device
+    out = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_boundary_f1(counts.data_ptr(), B, int(tolerance), float(smooth), out.data_ptr(), _stream_ptr(dev))
+    _lib.check(st, "pil_boundary_f1")
+    return out
+
+
 def forward_pointwise_xchg(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, ex: "_lib.PilExchange",
                            sums: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K1L + push of the shard's sums into every rank's mailbox (include/pil.h pil_forward_pointwise_xchg)."""
@@ -417,6 +460,67 @@ def loss_fwd_bwd(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, gra
                                          _stream_ptr(dev))
     _lib.check(st, "pil_loss_fwd_bwd")
     return report, sums, grad
+
+
+class StepGraph:
+    """One training-step evaluation (pointwise forward -> backward with stencil sums and loss report) as ONE
+    CUDA-graph launch (include/pil.h pil_step_graph_*).  The graph is bound to `x`, `t` and `grad`: refill x and t in
+    place (copy_) between launches.  With `exchange` (a sharding.PeerExchange created with device_epoch=True) x and t
+    are this rank's shard and `report` / `sums` describe the GLOBAL batch; construction is then collective and
+    performs one real step.  `launch()` enqueues the step on the current stream and returns `report` (float32[8],
+    device, no sync)."""
+
+    def __init__(self, x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, grad: Optional[torch.Tensor] = None,
+                 exchange=None, n_global: int = -1, grad_scale: float = 1.0, upstream: Optional[torch.Tensor] = None):
+        p.validate()
+        B, H, W = check_maps(x, t)
+        dev = x.device
+        self.x, self.t = x, t
+        self.grad = torch.empty_like(x) if grad is None else grad
+        self.sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)      # single shard: complete; sharded: this shard's pointwise sums
+        self.total = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev) if exchange is not None else self.sums
+        self.stencil = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+        self.report = torch.empty(PIL_NOUT, dtype=torch.float32, device=dev)
+        self.upstream = None
+        if upstream is not None:
+            self.upstream = upstream.to(device=dev, dtype=torch.float32).reshape(1)
+        # a private workspace: the graph keeps its address
+        self._ws = torch.zeros(max(_lib.lib().pil_workspace_bytes(B, H, W), 1 << 12), dtype=torch.uint8, device=dev)
+        self._ex = None
+        if exchange is not None:
+            if not getattr(exchange, "device_epoch", False):
+                raise ValueError("StepGraph needs a PeerExchange created with device_epoch=True")
+            self._ex = exchange.next_step()
+            self._exchange = exchange  # keeps the mailboxes mapped
+        single = exchange is None and upstream is None and grad_scale == 1.0
+        cp = p.c()
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            st = _lib.lib().pil_step_graph_create(
+                ctypes.byref(self._h), x.data_ptr(), t.data_ptr(), self.grad.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                ctypes.byref(cp), self.sums.data_ptr(), self.report.data_ptr(), self.stencil.data_ptr(), self._ws.data_ptr(),
+                self._ws.numel(), ctypes.byref(self._ex) if self._ex is not None else None,
+                int(B * H * W if exchange is None else n_global), self.upstream.data_ptr() if self.upstream is not None else None,
+                float(grad_scale), self.total.data_ptr() if (exchange is not None or single) else None, _stream_ptr(dev))
+        _lib.check(st, "pil_step_graph_create")
+        self._dev = dev
+
+    def launch(self) -> torch.Tensor:
+        with torch.cuda.device(self._dev):
+            st = _lib.lib().pil_step_graph_launch(self._h, _stream_ptr(self._dev))
+        _lib.check(st, "pil_step_graph_launch")
+        return self.report
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().pil_step_graph_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def scale_gradient(grad: torch.Tensor, upstream: torch.Tensor) -> torch.Tensor:

@@ -31,6 +31,8 @@ _METRIC_NAMES = {
     "compute_dice_score_batch": _metrics.compute_dice_score_batch,
     "compute_iou": _metrics.compute_iou,
     "compute_iou_batch": _metrics.compute_iou_batch,
+    "compute_boundary_f1": _metrics.compute_boundary_f1,
+    "compute_boundary_f1_batch": _metrics.compute_boundary_f1_batch,
 }
 
 

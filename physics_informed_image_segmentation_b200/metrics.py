@@ -64,3 +64,22 @@ def compute_iou(predictions: torch.Tensor, targets: torch.Tensor, threshold: flo
     """IoU of the thresholded prediction over the whole batch, 0-dim (reference src/evaluate.py:26-59)."""
     _, iou = Fn.image_metrics(_global_counts(predictions, targets, threshold), smooth)
     return iou[0]
+
+
+def compute_boundary_f1_batch(predictions: torch.Tensor, targets: torch.Tensor, threshold: float = 0.5,
+                              tolerance: int = 2, smooth: float = 1e-6) -> torch.Tensor:
+    """Boundary-F1 within `tolerance` pixels for each sample, shape (B,) (reference src/evaluate.py:196-229).
+
+    The reference pulls every image to the host and runs OpenCV on it (findContours + drawContours, two
+    distanceTransform calls) -- B device-to-host syncs on every training step (src/train.py:156).  Here the same
+    boundary pixels and chamfer neighbourhoods are counted by CUDA kernels (include/pil.h pil_boundary_counts); the
+    result stays on the predictions' device (the reference returns a CPU tensor; `.cpu()` works on both)."""
+    counts = Fn.boundary_counts(predictions.detach(), targets.detach(), Fn.X_PROB, threshold, int(tolerance))
+    return Fn.boundary_f1(counts, int(tolerance), smooth)
+
+
+def compute_boundary_f1(predictions: torch.Tensor, targets: torch.Tensor, threshold: float = 0.5,
+                        tolerance: int = 2, smooth: float = 1e-6) -> torch.Tensor:
+    """Boundary-F1 of the FIRST sample, 0-dim -- the reference looks at `predictions[0, 0]` only
+    (src/evaluate.py:149-150)."""
+    return compute_boundary_f1_batch(predictions[:1].contiguous(), targets[:1].contiguous(), threshold, tolerance, smooth)[0]

@@ -46,7 +46,11 @@ class PeerExchange:
     ranks must call it in lock step, which a data-parallel loop does by construction.
     """
 
-    def __init__(self, device: torch.device, group=None):
+    def __init__(self, device: torch.device, group=None, device_epoch: bool = False):
+        """device_epoch: the step tag lives in a counter in each rank's own mailbox (PIL_XCHG_DEVICE_EPOCH) instead of
+        coming from the host with every call: the arguments of a step are then identical from step to step, which is
+        what lets functional.StepGraph replay a captured step.  The mode is fixed for the lifetime of the mailboxes
+        and must be the same on every rank."""
         import ctypes
 
         import torch.distributed as dist
@@ -82,6 +86,9 @@ class PeerExchange:
             self._peers[r] = ptr.value
             self._ex.mailbox[r] = ptr.value
         self._epoch = 0
+        self.device_epoch = bool(device_epoch)
+        if self.device_epoch:
+            self._ex.flags = _lib.PIL_XCHG_DEVICE_EPOCH
         dist.barrier(group=group)  # nobody pushes before every mailbox is mapped everywhere
 
     def next_step(self):
@@ -90,9 +97,10 @@ class PeerExchange:
 
         ex = _lib.PilExchange()
         ex.rank, ex.world, ex.epoch = self.rank, self.world, self._epoch
+        ex.flags = self._ex.flags
         for r in range(self.world):
             ex.mailbox[r] = self._ex.mailbox[r]
-        self._epoch += 1
+        self._epoch += 1  # device-epoch mode: informational only, the kernels count the steps themselves
         return ex
 
     def timed_out(self) -> bool:
@@ -132,11 +140,13 @@ def _group_key(group, device) -> tuple:
     return (id(g) if g is not None else 0, torch.device(device).index)
 
 
-def enable_peer_exchange(device: torch.device, group=None) -> PeerExchange:
+def enable_peer_exchange(device: torch.device, group=None, device_epoch: bool = False) -> PeerExchange:
     """Collective: create (once) the peer-memory exchange the fused loss uses for `group`."""
     key = _group_key(group, device)
     if key not in _EXCHANGES:
-        _EXCHANGES[key] = PeerExchange(device, group)
+        _EXCHANGES[key] = PeerExchange(device, group, device_epoch=device_epoch)
+    elif _EXCHANGES[key].device_epoch != bool(device_epoch):
+        raise RuntimeError("the peer exchange of this group already exists with a different epoch mode")
     return _EXCHANGES[key]
 
 
