@@ -173,6 +173,14 @@ int pil_loss_fwd_bwd(const void* x, const void* t, void* grad, int64_t B, int64_
                      int x_dtype, int t_dtype, int x_kind, const PilParams* p,
                      double* sums, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
 int pil_scale_gradient(void* grad, int dtype, int64_t n, const float* upstream, void* stream);
+/* pil_backward that returns at once when *upstream == 1 (decided on the device): `grad` already holds the gradient
+ * for a unit upstream (written by pil_loss_fwd_bwd / pil_backward_accumulate) and is recomputed in place, from the
+ * maps and in fp32, only for another upstream value.  For bf16 gradients, where rescaling the stored values would
+ * round twice. */
+int pil_backward_if_scaled(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W,
+                           int x_dtype, int t_dtype, int x_kind, const PilParams* p,
+                           const double* global_sums, int64_t n_global, const float* upstream, float grad_scale,
+                           void* stream);
 
 /*
  * Per-step accuracy metrics folded into the step.  train_epoch / validate compute, between

@@ -64,3 +64,22 @@ def evaluate():
         stub.CellSegmentationDataset = object
         sys.modules[f"{_PKG}.dataset"] = stub
     return _load("evaluate")
+
+
+def train():
+    """src/train.py (train_epoch, validate, train_stage).  It imports src/plot.py, which needs matplotlib -- not
+    installed here -- so a stub `matplotlib.pyplot` is registered first; nothing on the step path touches it."""
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    _load("pde")
+    _load("loss")
+    _load("unet")
+    evaluate()
+    _load("plot")
+    return _load("train")

@@ -13,12 +13,13 @@ from .sweep import sweep_losses, s2_grid, s3_grid
 from .metrics import (compute_dice_score, compute_dice_score_batch, compute_iou, compute_iou_batch, compute_boundary_f1,
                       compute_boundary_f1_batch)
 from .integration import install_into_reference, use_logits_head
+from .training import train_epoch, validate
 
 __all__ = [
     "DiceBCELoss", "DiceBCEPDELoss", "PDERegularization", "create_pde_regularization", "LossParams",
     "shard_bounds", "all_reduce_sums", "loss_report_from_sums", "HostSession",
     "install_into_reference", "use_logits_head", "sweep_losses", "s2_grid", "s3_grid",
     "compute_dice_score", "compute_dice_score_batch", "compute_iou", "compute_iou_batch",
-    "compute_boundary_f1", "compute_boundary_f1_batch",
+    "compute_boundary_f1", "compute_boundary_f1_batch", "train_epoch", "validate",
 ]
 __version__ = "0.1.0"

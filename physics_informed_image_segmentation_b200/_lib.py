@@ -157,6 +157,9 @@ _SIGS = {
     "pil_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                     ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PilParams),
                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]),
+    "pil_backward_if_scaled": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                              ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PilParams),
+                                              ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]),
     "pil_forward_pointwise": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PilParams),
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

@@ -415,7 +415,7 @@ int pil_finalize(const double* sums, int64_t n_global, const PilParams* p, float
 static int backward_impl(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
                          int x_kind, const PilParams* p, const double* global_sums, int64_t n_global, const float* upstream,
                          float grad_scale, double* stencil_sums, float* loss_out, double* total_sums, void* acc_ws,
-                         size_t acc_ws_bytes, void* stream, const PilExchange* ex = nullptr) {
+                         size_t acc_ws_bytes, void* stream, const PilExchange* ex = nullptr, bool skip_unit_upstream = false) {
     int st = check_common(x, t, B, H, W, x_dtype, t_dtype, x_kind, p);
     if (st != PIL_OK) return st;
     if (!grad || (!global_sums && !ex)) return PIL_ERR_NULL;
@@ -431,6 +431,7 @@ static int backward_impl(const void* x, const void* t, void* grad, int64_t B, in
     a.n_global = (long long)n_global;
     a.p = *p;
     a.accumulate = acc_ws != nullptr ? 1 : 0;
+    a.skip_unit_upstream = skip_unit_upstream ? 1 : 0;
     {
         static int rev = -1;
         if (rev < 0) {
@@ -480,6 +481,14 @@ int pil_backward(const void* x, const void* t, void* grad, int64_t B, int64_t H,
                  float grad_scale, void* stream) {
     return backward_impl(x, t, grad, B, H, W, x_dtype, t_dtype, x_kind, p, global_sums, n_global, upstream, grad_scale,
                          nullptr, nullptr, nullptr, nullptr, 0, stream);
+}
+
+int pil_backward_if_scaled(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                           int x_kind, const PilParams* p, const double* global_sums, int64_t n_global, const float* upstream,
+                           float grad_scale, void* stream) {
+    if (!upstream) return PIL_ERR_NULL;
+    return backward_impl(x, t, grad, B, H, W, x_dtype, t_dtype, x_kind, p, global_sums, n_global, upstream, grad_scale,
+                         nullptr, nullptr, nullptr, nullptr, 0, stream, nullptr, true);
 }
 
 int pil_backward_accumulate(const void* x, const void* t, void* grad, int64_t B, int64_t H, int64_t W, int x_dtype,

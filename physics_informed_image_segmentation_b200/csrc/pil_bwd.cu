@@ -138,6 +138,7 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
     pdl_wait();
     pdl_launch_dependents();
     TL_STAMP(1, 1);
+    if (A.skip_unit_upstream && A.upstream != nullptr && __ldg(A.upstream) == 1.0f) return;  // uniform: plain loss.backward()
 
     // ---- global sums: given, or (data parallel) collected from the peer mailbox -----------------
     // Every block waits here for all ranks' pointwise sums.  The rows this block starts with were already

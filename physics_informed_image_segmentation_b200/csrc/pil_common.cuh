@@ -473,6 +473,7 @@ struct BwdArgs {
     long long n_global;
     PilParams p;
     int reverse;  // walk the shard back to front (L2 reuse after the pointwise forward)
+    int skip_unit_upstream;  // pil_backward_if_scaled: nothing to do when *upstream == 1 (grad already holds that gradient)
     // accumulate mode (pil_backward_accumulate): the stencil sums the pointwise forward left out
     int accumulate;
     double* partials;

@@ -208,8 +208,9 @@ def finalize_report(sums: torch.Tensor, n_global: int, p: LossParams, report: Op
 
 def backward_grad(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, gsums: torch.Tensor, n_global: int,
                   upstream: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """K2.  grad = upstream * grad_scale * dL/dx, same dtype/shape as x."""
+                  out: Optional[torch.Tensor] = None, only_if_scaled: bool = False) -> torch.Tensor:
+    """K2.  grad = upstream * grad_scale * dL/dx, same dtype/shape as x.  only_if_scaled: `out` already holds the
+    gradient for upstream == 1; the kernel returns at once in that case (pil_backward_if_scaled)."""
     B, H, W = check_maps(x, t)
     L = _lib.lib()
     dev = x.device
@@ -221,11 +222,11 @@ def backward_grad(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, gs
             upstream = upstream.to(device=dev, dtype=torch.float32).reshape(1)
         up_ptr = upstream.data_ptr()
     cp = p.c()
+    fn = L.pil_backward_if_scaled if only_if_scaled else L.pil_backward
     with torch.cuda.device(dev):
-        st = L.pil_backward(x.data_ptr(), t.data_ptr(), out.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
-                            ctypes.byref(cp), gsums.data_ptr(), int(n_global), up_ptr, float(grad_scale),
-                            _stream_ptr(dev))
-    _lib.check(st, "pil_backward")
+        st = fn(x.data_ptr(), t.data_ptr(), out.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                ctypes.byref(cp), gsums.data_ptr(), int(n_global), up_ptr, float(grad_scale), _stream_ptr(dev))
+    _lib.check(st, "pil_backward_if_scaled" if only_if_scaled else "pil_backward")
     return out
 
 
@@ -557,41 +558,46 @@ def _params_for(p: LossParams, which: int) -> LossParams:
 
 
 class _FusedLossFn(torch.autograd.Function):
-    """Training path.  Both halves of `loss = criterion(x, t); loss.backward()` are known to run, so the
-    forward launches the pointwise sums kernel AND the backward kernel (which also accumulates the two
-    stencil sums): every 5-point stencil is evaluated once per step, and the loss report is complete
-    when forward returns.  backward() only applies the upstream scalar (a no-op kernel when it is 1).
+    """Training path.  Both halves of `loss = criterion(x, t); loss.backward()` are known to run, so (eager=True) the
+    forward launches the pointwise sums kernel AND the backward kernel (which also accumulates the two stencil sums):
+    every 5-point stencil is evaluated once per step, and the loss report is complete when forward returns.
+    backward() then only applies the upstream scalar (a no-op kernel when it is 1).  The price is a full-size gradient
+    buffer parked on the graph whether or not .backward() is ever called; eager=False (component evaluations such as
+    criterion.bce(...) or pde_regularization.compute_loss(...), and criterion.lazy_backward = True) runs the full
+    forward kernel only and computes the gradient on demand from the saved sums.
 
-    Returns the requested report entry plus the whole report vector (float32[8]), so one evaluation
-    serves the total loss AND the four logged components (reference src/train.py:120-150)."""
+    x is saved through save_for_backward WITHOUT detaching, so an in-place change of x between forward and backward
+    raises autograd's usual version-counter error instead of returning a stale gradient.
+
+    Returns the requested report entry plus the whole report vector (float32[8]), so one evaluation serves the total
+    loss AND the four logged components (reference src/train.py:120-150)."""
 
     @staticmethod
-    def forward(ctx, x, t, p: LossParams, kind: int, which: int, group, ddp_average: bool, metrics_thr=None):
+    def forward(ctx, x, t, p: LossParams, kind: int, which: int, group, ddp_average: bool, metrics_thr=None, eager: bool = True):
         x_d = x.detach()
         t_d = t.detach()
         pg = _params_for(p, which)  # the gradient is that of the requested entry
         counts = None
-        if metrics_thr is not None and group is None:
-            # per-image threshold counts ride on the pointwise forward (K1M), then the usual backward
-            sums, counts = forward_pointwise_metrics(x_d, t_d, pg, kind, metrics_thr)
-            report = torch.empty(PIL_NOUT, dtype=torch.float32, device=x_d.device)
-            stencil = torch.empty(PIL_NSUMS, dtype=torch.float64, device=x_d.device)
-            grad, _ = backward_accumulate(x_d, t_d, pg, kind, sums, x_d.numel(), stencil_sums=stencil, report=report)
-            sums = sums + stencil
-            if pg is not p:
-                report = finalize_report(sums, x_d.numel(), p)
-            ctx.save_for_backward(x_d, t_d, sums)
-            ctx.grad = grad
-            ctx.p, ctx.kind, ctx.n_global, ctx.scale = pg, kind, x_d.numel(), 1.0
-            ctx.mark_non_differentiable(report, counts)
-            return report[which], report, counts
+        dev = x_d.device
+        scale, n_global = 1.0, x_d.numel()
+        grad = None
         if group is not None:
             import torch.distributed as dist
 
             scale = float(dist.get_world_size(group)) if ddp_average else 1.0
+            n_global = -1
+        if not eager:
+            # forward only: all six sums from the full forward kernel, no gradient buffer
+            if metrics_thr is not None:
+                _, counts = forward_pointwise_metrics(x_d, t_d, pg, kind, metrics_thr)
+            sums, _ = forward_sums(x_d, t_d, pg, kind, finalize=False)
+            if group is not None:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            report = finalize_report(sums, n_global, p)
+        elif group is not None:
             from .sharding import peer_exchange_for
 
-            px = peer_exchange_for(group, x_d.device)
+            px = peer_exchange_for(group, dev)
             if px is not None and pg is p:
                 # peer-memory path: the two kernels swap their sums over NVLink themselves (no NCCL call)
                 ex = px.next_step()
@@ -600,57 +606,64 @@ class _FusedLossFn(torch.autograd.Function):
                 else:
                     forward_pointwise_xchg(x_d, t_d, pg, kind, ex)
                 grad, report, sums = backward_accumulate_xchg(x_d, t_d, pg, kind, ex, -1, grad_scale=scale)
-                ctx.save_for_backward(x_d, t_d, sums)
-                ctx.grad = grad
-                ctx.p, ctx.kind, ctx.n_global, ctx.scale = pg, kind, -1, scale
-                if counts is None:
-                    counts = torch.empty(0, 4, dtype=torch.float64, device=x_d.device)
-                ctx.mark_non_differentiable(report, counts)
-                return report[which], report, counts
-            if metrics_thr is not None:
-                sums, counts = forward_pointwise_metrics(x_d, t_d, pg, kind, metrics_thr)
             else:
-                sums = forward_pointwise(x_d, t_d, pg, kind)
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)           # the gradient needs global I, P, T
-            grad, stencil = backward_accumulate(x_d, t_d, pg, kind, sums, -1, grad_scale=scale)
-            dist.all_reduce(stencil, op=dist.ReduceOp.SUM, group=group)        # only the loss VALUE needs these
+                if metrics_thr is not None:
+                    sums, counts = forward_pointwise_metrics(x_d, t_d, pg, kind, metrics_thr)
+                else:
+                    sums = forward_pointwise(x_d, t_d, pg, kind)
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)           # the gradient needs global I, P, T
+                grad, stencil = backward_accumulate(x_d, t_d, pg, kind, sums, -1, grad_scale=scale)
+                dist.all_reduce(stencil, op=dist.ReduceOp.SUM, group=group)        # only the loss VALUE needs these
+                sums = sums + stencil
+                report = finalize_report(sums, -1, p)
+        elif metrics_thr is not None:
+            # per-image threshold counts ride on the pointwise forward (K1M), then the usual backward
+            sums, counts = forward_pointwise_metrics(x_d, t_d, pg, kind, metrics_thr)
+            report = torch.empty(PIL_NOUT, dtype=torch.float32, device=dev)
+            stencil = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+            grad, _ = backward_accumulate(x_d, t_d, pg, kind, sums, x_d.numel(), stencil_sums=stencil, report=report)
             sums = sums + stencil
-            report = finalize_report(sums, -1, p)
-            n_global = -1
+            if pg is not p:
+                report = finalize_report(sums, x_d.numel(), p)
         else:
             report, sums, grad = loss_fwd_bwd(x_d, t_d, pg, kind)
             if pg is not p:
                 report = finalize_report(sums, x_d.numel(), p)
-            scale, n_global = 1.0, x_d.numel()
-        ctx.save_for_backward(x_d, t_d, sums)
+        ctx.save_for_backward(x, t, sums)  # x itself, not a detached alias: keeps autograd's in-place check alive
         ctx.grad = grad
         ctx.p, ctx.kind, ctx.n_global, ctx.scale = pg, kind, n_global, scale
         if counts is None:
-            counts = torch.empty(0, 4, dtype=torch.float64, device=x_d.device)
+            counts = torch.empty(0, 4, dtype=torch.float64, device=dev)
         ctx.mark_non_differentiable(report, counts)
         return report[which], report, counts
 
     @staticmethod
     def backward(ctx, g_loss, _g_report, _g_counts):
+        x, t, sums = ctx.saved_tensors  # raises if x or t was modified in place since forward
         grad = ctx.grad
+        none8 = (None,) * 8
         if grad is not None:
-            ctx.grad = None  # the buffer is scaled in place, so it can be handed out once
-            return scale_gradient(grad, g_loss), None, None, None, None, None, None, None
-        # second backward through a retained graph: recompute from the saved global sums
-        x, t, sums = ctx.saved_tensors
-        grad = backward_grad(x, t, ctx.p, ctx.kind, sums, ctx.n_global, upstream=g_loss, grad_scale=ctx.scale)
-        return grad, None, None, None, None, None, None, None
+            ctx.grad = None  # the buffer is handed out (and possibly scaled in place) once
+            if grad.dtype == torch.bfloat16:
+                # the eager buffer is already rounded to bf16: rescaling it would round twice.  The kernel decides on
+                # the device: upstream == 1 (plain loss.backward()) -> nothing to do; otherwise recomputed in fp32.
+                return (backward_grad(x.detach(), t.detach(), ctx.p, ctx.kind, sums, ctx.n_global, upstream=g_loss,
+                                      grad_scale=ctx.scale, out=grad, only_if_scaled=True),) + none8
+            return (scale_gradient(grad, g_loss),) + none8
+        # lazy evaluation, or a second backward through a retained graph: from the saved global sums
+        grad = backward_grad(x.detach(), t.detach(), ctx.p, ctx.kind, sums, ctx.n_global, upstream=g_loss, grad_scale=ctx.scale)
+        return (grad,) + none8
 
 
 def fused_loss_with_counts(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int = X_PROB, which: int = OUT_TOTAL,
-                           group=None, ddp_average: bool = True, metrics_threshold: Optional[float] = None):
+                           group=None, ddp_average: bool = True, metrics_threshold: Optional[float] = None, eager: bool = True):
     """(requested scalar with grad_fn, detached report float32[8], per-image counts float64[B,4] or None).
     With metrics_threshold the per-image threshold counts of this rank's images come from the same pass
     over the maps in the training path; the no-grad path spends one extra pointwise pass on them."""
     p.validate()
     check_maps(x, t)
     if x.requires_grad and torch.is_grad_enabled():
-        loss, report, counts = _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average, metrics_threshold)
+        loss, report, counts = _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average, metrics_threshold, eager)
         if metrics_threshold is None:
             return loss, report, None
         remember_counts(x, t, kind, metrics_threshold, counts)
@@ -664,12 +677,13 @@ def fused_loss_with_counts(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind
 
 
 def fused_loss(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int = X_PROB, which: int = OUT_TOTAL,
-               group=None, ddp_average: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(requested scalar with grad_fn, detached report float32[8])."""
+               group=None, ddp_average: bool = True, eager: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(requested scalar with grad_fn, detached report float32[8]).  eager=False: no gradient buffer is computed unless
+    .backward() is actually called (component / logging evaluations)."""
     p.validate()
     check_maps(x, t)
     if x.requires_grad and torch.is_grad_enabled():
-        loss, report, _ = _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average, None)
+        loss, report, _ = _FusedLossFn.apply(x, t, p, kind, which, group, ddp_average, None, eager)
         return loss, report
     # no graph needed (validation / logging): skip the autograd.Function overhead
     if group is not None:

@@ -36,16 +36,23 @@ _METRIC_NAMES = {
 }
 
 
-def install_into_reference(package: str = "src", track_metrics: bool = True) -> list:
+def install_into_reference(package: str = "src", track_metrics: bool = True, fused_step: bool = True) -> list:
     """Rebind the loss/PDE names inside the imported reference package.  Returns the list of
-    (module, name) pairs that were replaced.  With track_metrics (default) the four thresholded Dice/IoU
+    (module, name) pairs that were replaced.  With track_metrics (default) the thresholded Dice/IoU and boundary-F1
     functions are rebound too and every criterion built afterwards leaves per-image threshold counts
-    (threshold 0.5, the value the reference passes), so those per-step metric calls cost no pass over the maps."""
+    (threshold 0.5, the value the reference passes), so those per-step metric calls cost no pass over the maps.
+    With fused_step (default) `train_epoch` and `validate` (src/train.py:84-286) are replaced by training.train_epoch /
+    training.validate: logits head + fused activation, components and metrics from the loss's own kernels, one host
+    sync per epoch; train_stage (src/train.py:289-391) picks them up through the module's globals."""
     replaced = []
     names = dict(_NAMES)
     if track_metrics:
         names.update(_METRIC_NAMES)
         _FusedLossBase.default_batch_metrics_threshold = 0.5
+    if fused_step:
+        from . import training as _training
+
+        names.update({"train_epoch": _training.train_epoch, "validate": _training.validate})
     _names_backup = names
     for modname, mod in list(sys.modules.items()):
         if mod is None or not (modname == package or modname.startswith(package + ".")):

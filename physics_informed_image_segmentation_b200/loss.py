@@ -38,7 +38,7 @@ class _FusedBCE(nn.Module):
             if cached is not None:
                 return cached
         p = LossParams(dice_weight=0.0, bce_weight=1.0, pde_weight=0.0, phase_field_weight=0.0)
-        out, _ = Fn.fused_loss(predictions, targets, p, Fn.X_PROB, Fn.OUT_BCE)
+        out, _ = Fn.fused_loss(predictions, targets, p, Fn.X_PROB, Fn.OUT_BCE, eager=False)  # logging call: gradient on demand
         return out
 
 
@@ -60,6 +60,10 @@ class _FusedLossBase(nn.Module):
         # return a NaN loss without a host sync; with strict_inputs=True the module also raises the reference's
         # RuntimeError, at the price of one sync per call (the reference's loop syncs anyway at loss.item()).
         self.strict_inputs: bool = False
+        # False (default): a grad-enabled forward also runs the backward kernel, so the stencils are evaluated once per
+        # step and loss.backward() is free -- at the price of a full-size gradient buffer per forward even if
+        # .backward() never comes.  True: forward only; the gradient is computed when autograd asks for it.
+        self.lazy_backward: bool = False
         self._last_counts: Optional[torch.Tensor] = None
 
     def _params(self) -> LossParams:
@@ -68,7 +72,7 @@ class _FusedLossBase(nn.Module):
     def _run(self, x: torch.Tensor, t: torch.Tensor, kind: int) -> torch.Tensor:
         p = self._params()
         loss, report, counts = Fn.fused_loss_with_counts(x, t, p, kind, Fn.OUT_TOTAL, self.process_group, self.ddp_average,
-                                                         self.batch_metrics_threshold)
+                                                         self.batch_metrics_threshold, eager=not self.lazy_backward)
         self.last_report = report
         self._last_counts = counts
         if self.strict_inputs and kind == Fn.X_PROB and report[Fn.OUT_INVALID].item() > 0:

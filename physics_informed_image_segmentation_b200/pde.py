@@ -67,7 +67,7 @@ class PDERegularization(nn.Module):
             return cached
         # the kernels read a target map; with every target-dependent weight at 0 the prediction map
         # itself is a valid stand-in (same size, already resident in cache)
-        out, _ = Fn.fused_loss(u, u, self._params(pde_weight=1.0), Fn.X_PROB, Fn.OUT_RD)
+        out, _ = Fn.fused_loss(u, u, self._params(pde_weight=1.0), Fn.X_PROB, Fn.OUT_RD, eager=False)
         return out
 
     def compute_phase_field_loss(self, u: torch.Tensor, epsilon: float = 0.05) -> torch.Tensor:
@@ -77,7 +77,7 @@ class PDERegularization(nn.Module):
         cached = self._from_owner(u, Fn.OUT_PF, epsilon)
         if cached is not None:
             return cached
-        out, _ = Fn.fused_loss(u, u, self._params(phase_field_weight=1.0, epsilon=epsilon), Fn.X_PROB, Fn.OUT_PF)
+        out, _ = Fn.fused_loss(u, u, self._params(phase_field_weight=1.0, epsilon=epsilon), Fn.X_PROB, Fn.OUT_PF, eager=False)
         return out
 
     def _from_owner(self, u: torch.Tensor, which: int, epsilon):
