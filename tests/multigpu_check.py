@@ -84,6 +84,58 @@ def main():
         assert rel_scalar(sw[k, 0].item(), po.finalize(s, int(s[7]), pp)[0]) < 1e-5, k
     px = sharding.peer_exchange_for(None, dev)
     assert px is not None and not px.timed_out()
+
+    # ---- DDP: the averaged PARAMETER gradient of a conv model under ddp_average=True equals the single-process gradient
+    # on the concatenated batch, through the fused train step and the peer exchange
+    from tests.step_model import TinySegNet, make_batches
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    Bg = 4 * world
+    (images, masks), = make_batches(1, Bg, 64, 96, seed=21)
+    g0, g1 = sharding.shard_bounds(Bg, rank, world)
+    torch.manual_seed(7)
+    ref_model = TinySegNet(4, "sigmoid").to(dev)
+    ddp_model = DDP(TinySegNet(4, "sigmoid").to(dev), device_ids=[local])
+    ddp_model.module.load_state_dict(ref_model.state_dict())
+    crit_ref = P.DiceBCEPDELoss(**kw).to(dev)
+    crit_ddp = P.DiceBCEPDELoss(**kw, process_group=dist.group.WORLD, ddp_average=True).to(dev)
+    opt_ref = torch.optim.SGD(ref_model.parameters(), lr=0.0)
+    opt_ddp = torch.optim.SGD(ddp_model.parameters(), lr=0.0)
+    r_ref = P.train_epoch(ref_model, [(images, masks)], crit_ref, opt_ref, dev, return_components=True, compute_metrics=True)
+    r_ddp = P.train_epoch(ddp_model, [(images[g0:g1], masks[g0:g1])], crit_ddp, opt_ddp, dev, return_components=True, compute_metrics=True)
+    for (n1, p1), (n2, p2) in zip(ref_model.named_parameters(), ddp_model.module.named_parameters()):
+        assert rel_max(p2.grad.cpu().numpy(), p1.grad.cpu().numpy()) < 1e-5, ("ddp parameter gradient", n1)
+    for k in r_ref:
+        assert rel_scalar(r_ddp[k], r_ref[k]) < (1e-5 if not k.endswith("_score") else 1e-6), ("ddp epoch result", k, r_ddp[k], r_ref[k])
+    sharding.disable_peer_exchange()
+    dist.barrier()
+
+    # ---- one CUDA-graph launch per step over the device-epoch exchange == the direct exchange path (which ran the
+    # metrics variant of the pointwise kernel: another summation order, so equal to fp32 rounding, not bit for bit)
+    pxd = sharding.enable_peer_exchange(dev, None, device_epoch=True)
+    xs, ts = z[b0:b1].to(dev).contiguous(), t[b0:b1].to(dev).contiguous()
+    lp = P.LossParams(**kw)
+    graph = Fn.StepGraph(xs, ts, lp, Fn.X_LOGITS_SIGMOID, exchange=pxd, n_global=B * H * W, grad_scale=1.0)
+    for step in range(4):
+        rep_g = graph.launch().clone()
+    torch.cuda.synchronize()
+    for k in range(5):
+        assert rel_scalar(rep_g[k].item(), results["peer"][k].item()) < 2e-6, ("graph", k, rep_g, results["peer"])
+        assert rel_scalar(rep_g[k].item(), comps[k]) < 1e-5, ("graph vs oracle", k)
+    gathered = [torch.empty_like(rep_g) for _ in range(world)]
+    dist.all_gather(gathered, rep_g)
+    for gr in gathered:
+        assert torch.equal(gr[:5], rep_g[:5]), "every rank holds the same global report"
+    assert rel_max(graph.grad.cpu().numpy(), og[b0:b1]) < 1e-5
+    # the host-buffer session over the same exchange: global report, gradient of the shard on the device
+    with P.HostSession(b1 - b0, H, W, device=local) as sess:
+        for step in range(2):
+            rep_h = sess.run_sharded(z[b0:b1].numpy(), t[b0:b1].numpy(), lp, pxd, n_global=B * H * W)
+        for k in range(5):
+            assert rel_scalar(float(rep_h[k]), comps[k]) < 1e-5, ("session", k, rep_h)
+        assert rel_max(sess.device_gradient().cpu().numpy(), og[b0:b1]) < 1e-5
+    assert not pxd.timed_out()
+    graph.close()
     sharding.disable_peer_exchange()
     dist.barrier()
     if rank == 0:
