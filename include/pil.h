@@ -226,6 +226,30 @@ int pil_boundary_counts(const void* x, const void* t, int64_t B, int64_t H, int6
 int pil_boundary_f1(const long long* counts, int64_t B, int tolerance, double smooth, float* f1_out, void* stream);
 
 /*
+ * The model tail fused with the loss: the U-Net's 1x1 output convolution from its C-channel
+ * full-resolution features to one channel (src/unet.py:157, :205), its output activation (:208-214) and the loss.
+ *   pil_tail_forward   z = sum_c weight[c] * feat[b,c,h,w] + bias, written once as fp32 logits (B,1,H,W), AND the
+ *                      pointwise sums of pil_forward_pointwise on the same registers (sums; pushed to the peers
+ *                      when ex != NULL) -- one pass over the features replaces the convolution, the activation
+ *                      kernel and the pointwise forward.  x_kind: PIL_X_LOGITS_SIGMOID or PIL_X_LOGITS_TANH.
+ *   (then pil_backward_accumulate[_xchg] on logits_out, which yields grad_logits = dL/dlogits and the loss report)
+ *   pil_tail_backward  ONE pass over the features: grad_feat[b,c,h,w] = weight[c] * grad_logits[b,h,w] (same dtype
+ *                      as feat), grad_weight[c] = sum grad_logits * feat[.,c,.,.], grad_bias = sum grad_logits
+ *                      (deterministic two-level reduction) -- replaces the convolution backward's three kernels.
+ * feat: device, contiguous NCHW (B, C, H, W), PIL_F32 or PIL_BF16, 1 <= C <= 128; weight / bias / grad_weight /
+ * grad_bias: device fp32 (bias, grad_bias may be NULL).  Both kernels are bound by the feature traffic (C * 4 bytes
+ * per pixel each way); the fusion saves the logits / probability round trips and four launches.
+ */
+size_t pil_tail_workspace_bytes(int64_t C);
+int pil_tail_forward(const void* feat, int feat_dtype, const float* weight, const float* bias, const void* t, int t_dtype,
+                     int64_t B, int64_t C, int64_t H, int64_t W, int x_kind, const PilParams* p,
+                     float* logits_out, double* sums, void* workspace, size_t workspace_bytes,
+                     const struct PilExchange* ex /* may be NULL */, void* stream);
+int pil_tail_backward(const void* feat, int feat_dtype, const float* weight, const float* grad_logits,
+                      int64_t B, int64_t C, int64_t H, int64_t W, void* grad_feat, float* grad_weight, float* grad_bias,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Parameter sweeps (BASELINE config 4; the S2/S3 sensitivity grids of run_ablation.py:159-224 evaluated as
  * ONE batched loss evaluation).  lap(u), g = u(1-u), h = g*u, |grad u|^2 and the Dice/BCE sums do not
  * depend on D, a, eps or the weights, and r = D*lap + h - a*g, so the loss for ANY setting of the knobs is a

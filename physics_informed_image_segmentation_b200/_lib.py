@@ -223,6 +223,14 @@ _SIGS = {
                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "pil_boundary_f1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "pil_tail_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
+    "pil_tail_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                        ctypes.POINTER(PilParams), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.POINTER(PilExchange), ctypes.c_void_p]),
+    "pil_tail_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "pil_last_launch_info": (ctypes.c_int, [ctypes.POINTER(PilLaunchInfo)]),
     "pil_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "pil_set_l2_keep_mb": (ctypes.c_int, [ctypes.c_int]),

@@ -230,7 +230,7 @@ static unsigned long long xchg_timeout_ns() {
     }
     return v;
 }
-static int make_xchg(const PilExchange* ex, XchgDev* X) {
+int make_xchg(const PilExchange* ex, XchgDev* X) {
     *X = XchgDev{};
     if (!ex) return PIL_OK;
     if (ex->world < 1 || ex->world > PIL_MAX_RANKS || ex->rank < 0 || ex->rank >= ex->world) return PIL_ERR_EXCHANGE;

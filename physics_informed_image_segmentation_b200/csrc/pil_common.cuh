@@ -898,6 +898,9 @@ inline cudaError_t launch_pdl(K kernel, int blocks, int threads, int smem, cudaS
 // qualify (TMA needs a 16-byte aligned base and row pitch) or the driver entry point is unavailable.  pil_api.cu
 bool make_tensor_map_2d(CUtensorMap* out, const void* base, int dtype, long long rows, long long cols, int box_rows, int box_cols);
 
+// PilExchange (include/pil.h) -> the descriptor the kernels take; PIL_ERR_EXCHANGE for a bad one.  pil_api.cu
+int make_xchg(const PilExchange* ex, XchgDev* X);
+
 // per-kind launchers, one translation unit each in release builds (pil_fwd.cu, pil_point.cu, pil_bwd.cu)
 #define PIL_DECL_KIND(K)                                                                                                        \
     cudaError_t launch_fwd_k##K(int x_dtype, int t_dtype, FwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned,            \

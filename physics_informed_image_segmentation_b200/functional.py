@@ -655,6 +655,120 @@ class _FusedLossFn(torch.autograd.Function):
         return (grad,) + none8
 
 
+_TAIL_WS = {}
+
+
+def _tail_workspace(dev: torch.device, C: int) -> torch.Tensor:
+    key = (dev.index, _stream_ptr(dev), C)
+    ws = _TAIL_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.lib().pil_tail_workspace_bytes(C), dtype=torch.uint8, device=dev)
+        _TAIL_WS[key] = ws
+    return ws
+
+
+def _check_tail(feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], t: torch.Tensor):
+    if not feat.is_cuda:
+        raise RuntimeError("CUDA tensors only (no CPU fallback)")
+    if feat.dim() != 4 or not feat.is_contiguous():
+        raise RuntimeError("features must be a contiguous NCHW tensor (B, C, H, W); call .contiguous() on channels_last maps")
+    B, C, H, W = feat.shape
+    if not (1 <= C <= 128):
+        raise RuntimeError(f"the fused model tail supports 1..128 feature channels, got {C}")
+    if weight.numel() != C or weight.dtype != torch.float32 or not weight.is_contiguous() or weight.device != feat.device:
+        raise RuntimeError(f"weight must hold the {C} float32 values of the (1, {C}, 1, 1) output-convolution kernel on {feat.device}")
+    if bias is not None and (bias.numel() != 1 or bias.dtype != torch.float32 or bias.device != feat.device):
+        raise RuntimeError("bias must be one float32 value on the features' device")
+    if tuple(t.shape) not in ((B, 1, H, W), (B, H, W)) or t.device != feat.device or not t.is_contiguous():
+        raise ValueError(f"targets must be contiguous (B,1,H,W) maps on {feat.device}, got {tuple(t.shape)}")
+    if H < 2 or W < 2:
+        raise RuntimeError("reflect padding needs H >= 2 and W >= 2 (reference src/pde.py:67)")
+    return B, C, H, W
+
+
+class _TailLossFn(torch.autograd.Function):
+    """1x1 output convolution + activation + loss as ONE differentiable op over (features, weight, bias):
+    pil_tail_forward (convolution fused with the pointwise sums) -> the fused backward kernel on the logits ->
+    pil_tail_backward in backward() (dL/dfeatures, dL/dweight, dL/dbias from one pass over the features)."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, bias, t, p: LossParams, kind: int, group, ddp_average: bool):
+        fd, td = feat.detach(), t.detach()
+        B, C, H, W = _check_tail(fd, weight.detach(), bias.detach() if bias is not None else None, td)
+        dev = fd.device
+        L = _lib.lib()
+        logits = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+        sums = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+        ws = _tail_workspace(dev, C)
+        cp = p.c()
+        ex = None
+        scale, n_global = 1.0, B * H * W
+        if group is not None:
+            import torch.distributed as dist
+            from .sharding import peer_exchange_for
+
+            scale = float(dist.get_world_size(group)) if ddp_average else 1.0
+            n_global = -1
+            px = peer_exchange_for(group, dev)
+            ex = px.next_step() if px is not None else None
+        wd, bd = weight.detach().reshape(-1), (bias.detach().reshape(-1) if bias is not None else None)
+        with torch.cuda.device(dev):
+            st = L.pil_tail_forward(fd.data_ptr(), _x_dtype(fd), wd.data_ptr(), bd.data_ptr() if bd is not None else None,
+                                    td.data_ptr(), _t_dtype(td), B, C, H, W, kind, ctypes.byref(cp), logits.data_ptr(),
+                                    sums.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(ex) if ex is not None else None,
+                                    _stream_ptr(dev))
+        _lib.check(st, "pil_tail_forward")
+        if ex is not None:
+            gl, report, sums = backward_accumulate_xchg(logits, td, p, kind, ex, -1, grad_scale=scale)
+        elif group is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            gl, stencil = backward_accumulate(logits, td, p, kind, sums, -1, grad_scale=scale)
+            dist.all_reduce(stencil, op=dist.ReduceOp.SUM, group=group)
+            sums = sums + stencil
+            report = finalize_report(sums, -1, p)
+        else:
+            report = torch.empty(PIL_NOUT, dtype=torch.float32, device=dev)
+            stencil = torch.empty(PIL_NSUMS, dtype=torch.float64, device=dev)
+            gl, _ = backward_accumulate(logits, td, p, kind, sums, n_global, stencil_sums=stencil, report=report)
+        ctx.save_for_backward(feat, weight)
+        ctx.gl, ctx.has_bias, ctx.wshape = gl, bias is not None, weight.shape
+        ctx.mark_non_differentiable(report, logits)
+        return report[OUT_TOTAL], report, logits
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_report, _g_logits):
+        feat, weight = ctx.saved_tensors
+        gl = ctx.gl
+        if gl is None:
+            raise RuntimeError("the fused model tail keeps its logits gradient for one backward pass only")
+        ctx.gl = None
+        gl = scale_gradient(gl, g_loss)
+        fd = feat.detach()
+        B, C, H, W = fd.shape
+        dev = fd.device
+        dfeat = torch.empty_like(fd)
+        dw = torch.empty(C, dtype=torch.float32, device=dev)
+        db = torch.empty(1, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        ws = _tail_workspace(dev, C)
+        with torch.cuda.device(dev):
+            st = _lib.lib().pil_tail_backward(fd.data_ptr(), _x_dtype(fd), weight.detach().reshape(-1).data_ptr(), gl.data_ptr(),
+                                              B, C, H, W, dfeat.data_ptr(), dw.data_ptr(), db.data_ptr() if db is not None else None,
+                                              ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _lib.check(st, "pil_tail_backward")
+        return dfeat, dw.view(ctx.wshape), db, None, None, None, None, None
+
+
+def fused_tail_loss(feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], t: torch.Tensor, p: LossParams,
+                    kind: int = X_LOGITS_SIGMOID, group=None, ddp_average: bool = True):
+    """(loss with grad_fn over feat / weight / bias, detached report float32[8], detached fp32 logits (B,1,H,W))."""
+    p.validate()
+    if kind not in (X_LOGITS_SIGMOID, X_LOGITS_TANH):
+        raise ValueError("the fused model tail produces logits: activation must be 'sigmoid' or 'tanh'")
+    return _TailLossFn.apply(feat, weight, bias, t, p, kind, group, ddp_average)
+
+
 def fused_loss_with_counts(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int = X_PROB, which: int = OUT_TOTAL,
                            group=None, ddp_average: bool = True, metrics_threshold: Optional[float] = None, eager: bool = True):
     """(requested scalar with grad_fn, detached report float32[8], per-image counts float64[B,4] or None).

@@ -127,6 +127,25 @@ class _FusedLossBase(nn.Module):
         return self._run(logits, targets, Fn.activation_kind(activation))
 
 
+    def forward_features(self, features: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                         targets: torch.Tensor, activation: str = "sigmoid") -> torch.Tensor:
+        """The model tail fused in as well: `features` is the U-Net's C-channel full-resolution map
+        (contiguous NCHW), `weight` / `bias` the parameters of its 1x1 output convolution (src/unet.py:157, :205).  One
+        pass over the features computes the logits and the pointwise loss sums, the fused backward kernel the gradient
+        with respect to the logits, and loss.backward() one more pass for dL/dfeatures, dL/dweight and dL/dbias --
+        replacing out_conv, the activation, the loss passes over the logits and the convolution backward's three
+        kernels.  `last_logits` holds the fp32 logits (detached) for metrics."""
+        p = self._params()
+        loss, report, logits = Fn.fused_tail_loss(features, weight, bias, targets, p, Fn.activation_kind(activation),
+                                                  self.process_group, self.ddp_average)
+        self.last_report, self.last_logits = report, logits
+        self._last = None
+        if self.batch_metrics_threshold is not None:
+            _, self._last_counts = Fn.forward_pointwise_metrics(logits, targets.detach(), p, Fn.activation_kind(activation),
+                                                                self.batch_metrics_threshold)
+        return loss
+
+
 class DiceBCELoss(_FusedLossBase):
     """Batch-global soft Dice + mean BCE (reference src/loss.py:7-68)."""
 

@@ -93,9 +93,16 @@ def main():
     Bg = 4 * world
     (images, masks), = make_batches(1, Bg, 64, 96, seed=21)
     g0, g1 = sharding.shard_bounds(Bg, rank, world)
+    class F64Net(TinySegNet):
+        """fp64 convolutions, fp32 logits: the parameter gradients then differ between the two runs only by what the
+        LOSS gradient differs (the fp32 conv backward's own summation noise would dominate the comparison otherwise)"""
+
+        def forward(self, x):
+            return super().forward(x.double()).float()
+
     torch.manual_seed(7)
-    ref_model = TinySegNet(4, "sigmoid").to(dev)
-    ddp_model = DDP(TinySegNet(4, "sigmoid").to(dev), device_ids=[local])
+    ref_model = F64Net(4, "sigmoid").double().to(dev)
+    ddp_model = DDP(F64Net(4, "sigmoid").double().to(dev), device_ids=[local])
     ddp_model.module.load_state_dict(ref_model.state_dict())
     crit_ref = P.DiceBCEPDELoss(**kw).to(dev)
     crit_ddp = P.DiceBCEPDELoss(**kw, process_group=dist.group.WORLD, ddp_average=True).to(dev)
