@@ -591,7 +591,47 @@ def run_loss(args, C: Ctx):
             ms_m = e0.elapsed_time(e1) / Kx
             extras["module_api"] = {"value": B * H * W / (ms_m * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_m, "steps": Kx,
                                     "call": "loss = DiceBCEPDELoss.forward_logits(x, t); loss.backward()  (autograd, fresh gradient buffer per step)"}
-            del xm, crit
+            del xm
+            # the model tail: 64-channel features -> 1x1 output convolution -> activation -> loss -> backward,
+            # fused (criterion.forward_features) against torch's convolution around the fused loss
+            Bt, Ct = 8, 64
+            feat = torch.randn(Bt, Ct, H, W, device=C.dev)
+            conv = torch.nn.Conv2d(Ct, 1, 1).to(C.dev)
+            tt8 = t[:Bt].contiguous()
+
+            def tail_fused():
+                f = feat.requires_grad_(True)
+                f.grad = None
+                conv.zero_grad(set_to_none=True)
+                crit.forward_features(f, conv.weight, conv.bias, tt8).backward()
+
+            def tail_unfused():
+                f = feat.requires_grad_(True)
+                f.grad = None
+                conv.zero_grad(set_to_none=True)
+                crit.forward_logits(conv(f), tt8).backward()
+
+            tail = {}
+            for nm, fn in (("fused", tail_fused), ("torch_conv_plus_fused_loss", tail_unfused)):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tail[nm] = {"ms_per_step": e0.elapsed_time(e1) / 10}
+            px_t = Bt * H * W
+            fb = 4 * Ct  # feature bytes per pixel
+            tail["fused"]["algorithmic_bytes_per_pixel"] = fb + 4 + 4 + 12 + 4 + 2 * fb   # T1: feat + t + z | K2: z, t, g | T2: g + feat + dfeat
+            tail["fused"]["achieved_gbs"] = tail["fused"]["algorithmic_bytes_per_pixel"] * px_t / (tail["fused"]["ms_per_step"] * 1e-3) / 1e9
+            tail["note"] = (f"{Bt}x{Ct}x{H}x{W} fp32 features; both legs pay the three feature passes ({3 * fb} B/px); fusing the tail saves "
+                            "the logits round trips (~20 B/px) and the convolution's extra kernels, not feature traffic")
+            extras["model_tail"] = tail
+            del feat, conv, crit
+            torch.cuda.empty_cache()
 
     # ---- end to end through the host-buffer C ABI --------------------------------------------------------------
     e2e = None

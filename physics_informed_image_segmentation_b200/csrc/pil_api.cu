@@ -356,6 +356,9 @@ static int forward_impl(const void* x, const void* t, int64_t B, int64_t H, int6
     cudaStream_t s = (cudaStream_t)stream;
     const size_t avail = workspace_bytes - wl.partials_off;
     LaunchOut lo;
+    lo.task_counter = a.ticket + 1;
+    a.task_counter = nullptr;
+    a.first_dynamic = 0;
     cudaError_t e;
     switch (x_kind) {
         case PIL_X_PROB: e = launch_fwd_k0(x_dtype, t_dtype, a, B, H, W, aligned, avail, s, &lo, moments); break;
@@ -367,7 +370,7 @@ static int forward_impl(const void* x, const void* t, int64_t B, int64_t H, int6
     t_info.fwd_blocks = blocks;
     t_info.fwd_threads = kThreads;
     t_info.fwd_rows_per_segment = lo.rows;
-    t_info.fwd_aligned = aligned ? 1 : 0;
+    t_info.fwd_aligned = aligned ? (lo.tma ? 2 : 1) : 0;
     count_launch();
     return (int)e;
 }

@@ -305,9 +305,9 @@ struct TmaBox {
     static constexpr int kRowBytes = kCols * (int)sizeof(T);
     __device__ __forceinline__ static int first_col(int c0) { return c0 - (((c0 % kAlign) + kAlign) % kAlign); }
 };
-template <typename XT, typename TT>
+template <typename XT, typename TT, int ROWS = 6>
 struct TmaRing {
-    static constexpr int kBoxRows = 6;                     // == unroll factor of the steady-state loops
+    static constexpr int kBoxRows = ROWS;                  // rows per box == unroll factor of the steady-state loop that consumes it
     static constexpr int kXRowBytes = TmaBox<XT>::kRowBytes, kTRowBytes = TmaBox<TT>::kRowBytes;
     static constexpr int kXBoxBytes = kBoxRows * kXRowBytes, kTBoxBytes = kBoxRows * kTRowBytes;  // what the TMA unit delivers
     static constexpr int kXSlotBytes = (kXBoxBytes + 127) / 128 * 128, kTSlotBytes = (kTBoxBytes + 127) / 128 * 128;
@@ -460,6 +460,10 @@ struct FwdArgs {
     double* sums;            // [PIL_NSUMS]
     float* loss_out;         // may be null
     PilParams p;
+    // dynamic work distribution: after its first, statically assigned range a warp claims further (range, strip) tasks
+    // from this counter (null: one static task per warp); tasks [0, first_dynamic) are the static ones
+    unsigned int* task_counter;
+    long long first_dynamic;
 };
 
 struct BwdArgs {
@@ -656,29 +660,20 @@ static __device__ __noinline__ bool xchg_wait_sum(const XchgDev& X, int phase, d
 // *ticket to 0 when it is done (so the workspace is reusable by the next launch on the stream).
 // accumulator layout: 0 I, 1 P, 2 T, 3 bce (log2 units, un-negated), 4 r^2, 5 dx^2+dy^2, 6 (uv)^2, 7 #invalid
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, typename AccT, int N = PIL_NSUMS>
-__device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* partials, unsigned int* ticket, double* out) {
+// second level: the block's N doubles (thread k < N holds component k in `blk`) -> `partials` -> the LAST block to
+// finish (ticket) adds all blocks' partials in a fixed order.  Returns true in the last block only; there thread 0
+// holds the totals in out[].  The caller resets *ticket to 0 when it is done.
+template <int THREADS, int N>
+__device__ __forceinline__ bool blocks_to_last(double blk, double* partials, unsigned int* ticket, double* out) {
     constexpr int kWarps = THREADS / 32;
     constexpr int NP = N / 2;  // component pairs (16-byte loads)
     static_assert(N % 2 == 0 && THREADS % NP == 0 && (NP & (NP - 1)) == 0 && NP <= 32 && 32 % NP == 0, "component layout");
-    __shared__ double s_part[kWarps][N];
-    __shared__ double s_red[2 * THREADS];
+    __shared__ double s_red[kWarps * N];
     __shared__ double s_tot[N];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        AccT v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_part[warp][k] = (double)v;
-    }
-    __syncthreads();
     if (threadIdx.x < N) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) v += s_part[w][threadIdx.x];
-        partials[(long long)blockIdx.x * N + threadIdx.x] = v;
+        partials[(long long)blockIdx.x * N + threadIdx.x] = blk;
         __threadfence();
     }
     __syncthreads();
@@ -698,11 +693,11 @@ __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* pa
         const int c2 = threadIdx.x % NP, j = threadIdx.x / NP;
         const long long nb = gridDim.x;
         double vx = 0.0, vy = 0.0;
-        for (long long blk = j; blk < nb; blk += (long long)kIlp * kGroups) {
+        for (long long b0 = j; b0 < nb; b0 += (long long)kIlp * kGroups) {
             double2 w[kIlp];
 #pragma unroll
             for (int q = 0; q < kIlp; ++q) {
-                const long long b = blk + (long long)q * kGroups;
+                const long long b = b0 + (long long)q * kGroups;
                 w[q] = (b < nb) ? __ldcg(reinterpret_cast<const double2*>(partials + b * N) + c2) : make_double2(0.0, 0.0);
             }
 #pragma unroll
@@ -736,6 +731,28 @@ __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* pa
         for (int k = 0; k < N; ++k) out[k] = s_tot[k];
     }
     return true;
+}
+
+// first level: per-thread accumulators -> warp shuffles -> the block's doubles; then blocks_to_last
+template <int THREADS, typename AccT, int N = PIL_NSUMS>
+__device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* partials, unsigned int* ticket, double* out) {
+    constexpr int kWarps = THREADS / 32;
+    __shared__ double s_part[kWarps][N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        AccT v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][k] = (double)v;
+    }
+    __syncthreads();
+    double blk = 0.0;
+    if (threadIdx.x < N) {
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) blk += s_part[w][threadIdx.x];
+    }
+    return blocks_to_last<THREADS, N>(blk, partials, ticket, out);
 }
 
 // raw accumulator totals -> the sums vector of include/pil.h
@@ -849,6 +866,7 @@ struct LaunchOut {
     int status = PIL_OK;              // PIL_ERR_WORKSPACE when the partials do not fit
     size_t partials_avail = ~(size_t)0;  // in: bytes of the per-block partials area (backward, accumulate mode)
     int tma = 0;                         // out: rows staged by TMA boxes
+    unsigned int* task_counter = nullptr;  // in (forward): the workspace's task counter, for dynamic claiming
 };
 // Rows per range the kernels like best (measured on B200, 64x1024^2 .. 128x2048^2): long enough to
 // amortise the warm-up rows and the pipeline fill of a segment, short enough that the hardware block

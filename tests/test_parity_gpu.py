@@ -173,7 +173,7 @@ def test_unaligned_base_pointer(Fn, po, dev):
     sums, rep, g = gpu_loss_and_grad(Fn, x, tt, p, 1)
     assert Fn.launch_info().fwd_aligned == 0 and Fn.launch_info().bwd_aligned == 0
     sums2, rep2, g2 = gpu_loss_and_grad(Fn, z.to(dev), tt, p, 1)
-    assert Fn.launch_info().fwd_aligned == 1
+    assert Fn.launch_info().fwd_aligned in (1, 2)  # 1: cp.async ring, 2: TMA boxes
     assert rel_max(g, g2) < 1e-6 and rel_scalar(rep[0], rep2[0]) < 1e-6
 
 
