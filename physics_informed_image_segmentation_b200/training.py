@@ -84,6 +84,15 @@ def _results(criterion, acc: _EpochAccumulator, return_components: bool, compute
     """One device-to-host copy for the whole epoch, then the reference's result dictionary (src/train.py:169-185,
     :267-286)."""
     vec = torch.cat([acc.report, acc.metrics, acc.batch_dice])
+    if group is not None:
+        # the epoch's host sync is also where a peer-exchange time-out surfaces: a rank that lost its peers has been
+        # writing zero gradients and NaN losses since (include/pil.h); stop instead of training on
+        from .sharding import peer_exchange_for
+
+        px = peer_exchange_for(group, vec.device)
+        if px is not None and px.timed_out():
+            raise RuntimeError("a peer-memory exchange wait timed out during this epoch: a rank died or the ranks are not "
+                               "evaluating the loss in lock step (PIL_XCHG_TIMEOUT_MS)")
     if group is not None and compute_metrics:
         import torch.distributed as dist
 

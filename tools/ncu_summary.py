@@ -33,6 +33,12 @@ KEEP = [
     ("smsp__warps_eligible.avg.per_cycle_active", "eligible warps / scheduler"),
     ("smsp__warps_active.avg.per_cycle_active", "active warps / scheduler"),
     ("smsp__average_warp_latency_per_inst_issued.ratio", "warp cycles / issued inst"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe cycles active %"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe instructions %"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe instructions %"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe instructions %"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe instructions %"),
+    ("sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active", "TMA pipe instructions %"),
 ]
 
 
