@@ -790,18 +790,23 @@ def run_sweep(args, C: Ctx):
     reports = torch.empty(len(grid), 8, dtype=torch.float32, device=C.dev)
     kind = Fn.X_LOGITS_SIGMOID
     state = {"k": 0}
+    X = Exchanges(C, args.exchange)
 
     def step(events=None):
         zz, tt = sets[state["k"] % n_sets]
         state["k"] += 1
+        ex = X.host.next_step() if X.host is not None else None
         if events:
             events[0].record()
-        Fn.forward_moments(zz, tt, kind, moments=moments)
+        Fn.forward_moments(zz, tt, kind, moments=moments, ex=ex)
         if events:
             events[1].record()
-        if C.distributed:
-            C.dist.all_reduce(moments)
-        Fn.sweep_finalize(moments, n_global, grid, reports=reports)
+        if ex is not None:       # the moment sums crossed over peer memory inside the kernel: no collective call
+            Fn.sweep_finalize_xchg(ex, n_global, grid, C.dev, reports=reports)
+        else:
+            if C.distributed:
+                C.dist.all_reduce(moments)
+            Fn.sweep_finalize(moments, n_global, grid, reports=reports)
 
     sampler = ClockSampler(C.local_rank)
     if C.rank == 0:
@@ -857,7 +862,9 @@ def run_sweep(args, C: Ctx):
             "config": {"workload": f"{name}_{'fp32' if args.dtype == 'f32' else 'bf16'}", "global_batch": [B, 1, H, W],
                        "per_gpu_images": int(z.shape[0]), "settings_per_pass": len(grid),
                        "grids": "S2: D in {0.5,1,2,5,10,100} (pde_weight 1e-3); S3: eps in {0.001,0.01,0.05,0.1,0.2} (both weights 1e-4, D 5)",
-                       "step": "pil_forward_moments (one pass over x, t) -> all-reduce of 16 doubles -> pil_sweep_finalize (11 loss reports)",
+                       "step": ("pil_forward_moments_xchg (one pass over x, t; the shard's 16 sums pushed into every rank's mailbox) -> "
+                                "pil_sweep_finalize_xchg (11 global loss reports)") if X.host is not None else
+                               "pil_forward_moments (one pass over x, t) -> all-reduce of 16 doubles -> pil_sweep_finalize (11 loss reports)",
                        "l2_policy": ("maps %.0f MB per step > 2 x 126 MB L2" % (footprint / 1e6)) if n_sets == 1 else
                                     ("maps %.1f MB per step: steps rotate through %d buffer sets" % (footprint / 1e6, n_sets))},
             "pixel_evaluations_per_s": value * len(grid) * 1e9,
@@ -865,8 +872,9 @@ def run_sweep(args, C: Ctx):
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * esz * n_local, "kernel_ms": kern_ms,
                          "kernel_launches_timed": KA},
             "gpu_launches": int(launches), "clocks": clocks, "losses": [float(v) for v in reports[:, 0].cpu()],
-            **({"parity": parity} if parity else {}),
+            "exchange_timeout": X.timed_out(), **({"parity": parity} if parity else {}),
         })
+    X.close()
 
 
 def run_train_step(args, C: Ctx):

@@ -268,6 +268,17 @@ int pil_forward_moments(const void* x, const void* t, int64_t B, int64_t H, int6
                         double* moments, void* workspace, size_t workspace_bytes, void* stream);
 int pil_sweep_finalize(const double* moments, int64_t n_global, const PilParams* params, int n_params,
                        float* loss_out, void* stream);
+/* The sweep over a batch sharded across ranks, without a collective call: the last block of the moments kernel stores
+ * the shard's 16 sums into every rank's mailbox (two 8-double vectors, phases 0 and 1 of the PilExchange below);
+ * pil_sweep_finalize_xchg waits for all ranks' vectors in the LOCAL mailbox, adds them in rank order and writes the
+ * n_params (<= 32) loss reports of the GLOBAL batch, identical on every rank (moments_out: the global moments, may be
+ * NULL).  Same epoch discipline as the training step (one epoch per sweep step, host epochs only). */
+int pil_forward_moments_xchg(const void* x, const void* t, int64_t B, int64_t H, int64_t W,
+                             int x_dtype, int t_dtype, int x_kind,
+                             double* moments, void* workspace, size_t workspace_bytes,
+                             const struct PilExchange* ex, void* stream);
+int pil_sweep_finalize_xchg(const struct PilExchange* ex, int64_t n_global, const PilParams* params, int n_params,
+                            float* loss_out, double* moments_out, void* stream);
 
 /*
  * Data-parallel training step over PEER MEMORY (one process per GPU of one NVLink/NVSwitch node).

@@ -150,6 +150,11 @@ _SIGS = {
     "pil_forward_moments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_size_t, ctypes.c_void_p]),
+    "pil_forward_moments_xchg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_size_t, ctypes.POINTER(PilExchange), ctypes.c_void_p]),
+    "pil_sweep_finalize_xchg": (ctypes.c_int, [ctypes.POINTER(PilExchange), ctypes.c_int64, ctypes.POINTER(PilParams), ctypes.c_int,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pil_sweep_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(PilParams), ctypes.c_int,
                                           ctypes.c_void_p, ctypes.c_void_p]),
     "pil_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(PilParams), ctypes.c_void_p,

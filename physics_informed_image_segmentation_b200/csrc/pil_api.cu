@@ -48,6 +48,33 @@ __global__ void pil_sweep_finalize_kernel(const double* mo, long long n_global, 
     finalize_device(s, n_global > 0 ? (double)n_global : s[7], p, out + (size_t)k * PIL_NOUT);
 }
 
+// the same from the mailbox: the ranks' 16 moment sums arrive as two 8-double vectors (phases 0 and 1, pushed by the last
+// block of pil_forward_moments_xchg); the block adds them in rank order and evaluates the settings on the GLOBAL moments
+__global__ void __launch_bounds__(kThreads) pil_sweep_finalize_xchg_kernel(XchgDev X, long long n_global, SweepParams sp, float* out,
+                                                                           double* moments_out) {
+    __shared__ double s_mo[16];
+    const bool ok0 = xchg_wait_sum(X, 0, s_mo);
+    const bool ok1 = xchg_wait_sum(X, 1, s_mo + 8);
+    (void)ok0;
+    (void)ok1;  // a timed-out wait leaves NaN moments: every loss of the sweep is NaN and the status word is set
+    if (moments_out != nullptr && threadIdx.x < 16) moments_out[threadIdx.x] = s_mo[threadIdx.x];
+    const int k = threadIdx.x;
+    if (k >= sp.n) return;
+    const PilParams& p = sp.p[k];
+    const double D = p.diffusion_coeff, a = p.reaction_threshold, eps = p.epsilon;
+    const double* mo = s_mo;
+    double s[PIL_NSUMS];
+    s[0] = mo[0];
+    s[1] = mo[1];
+    s[2] = mo[2];
+    s[3] = mo[3];
+    s[4] = D * D * mo[4] + 2.0 * D * mo[8] - 2.0 * a * D * mo[9] + mo[10] - 2.0 * a * mo[11] + a * a * mo[6];
+    s[5] = (p.phase_field_weight > 0.0) ? 0.5 * eps * mo[5] + mo[6] / eps : 0.0;
+    s[6] = mo[7];
+    s[7] = mo[12];
+    finalize_device(s, n_global > 0 ? (double)n_global : s[7], p, out + (size_t)k * PIL_NOUT);
+}
+
 // stand-alone push of a sums vector into every rank's mailbox (pil_exchange_push): for callers that assemble the
 // shard's pointwise sums from several launches (the host-buffer session adds per-chunk sums first)
 __global__ void __launch_bounds__(kThreads) pil_xchg_push_kernel(XchgDev X, int phase, const double* sums) {
@@ -334,7 +361,7 @@ int pil_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
 
 static int forward_impl(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,
                         const PilParams* p, double* sums, float* loss_out, void* workspace, size_t workspace_bytes,
-                        void* stream, bool moments) {
+                        void* stream, bool moments, const PilExchange* ex = nullptr) {
     int st = check_common(x, t, B, H, W, x_dtype, t_dtype, x_kind, p);
     if (st != PIL_OK) return st;
     if (!sums || !workspace) return PIL_ERR_NULL;
@@ -351,6 +378,8 @@ static int forward_impl(const void* x, const void* t, int64_t B, int64_t H, int6
     a.sums = sums;
     a.loss_out = loss_out;
     a.p = *p;
+    st = make_xchg(ex, &a.X);
+    if (st != PIL_OK) return st;
     PIL_SET_BOUNDS(x, t, nullptr, B * H * W, x_dtype, t_dtype);
     const bool aligned = is_aligned_case(x, t, nullptr, W, x_dtype, t_dtype);
     cudaStream_t s = (cudaStream_t)stream;
@@ -386,6 +415,34 @@ int pil_forward_moments(const void* x, const void* t, int64_t B, int64_t H, int6
                         double* moments, void* workspace, size_t workspace_bytes, void* stream) {
     PilParams neutral = {0.5, 0.5, 0.0, 0.0, 1.0, 0.5, 1.0, 1e-6};  // the moments do not depend on any knob
     return forward_impl(x, t, B, H, W, x_dtype, t_dtype, x_kind, &neutral, moments, nullptr, workspace, workspace_bytes, stream, true);
+}
+
+int pil_forward_moments_xchg(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,
+                             double* moments, void* workspace, size_t workspace_bytes, const PilExchange* ex, void* stream) {
+    if (!ex) return PIL_ERR_NULL;
+    if (ex->flags & PIL_XCHG_DEVICE_EPOCH) return PIL_ERR_EXCHANGE;  // the sweep has no backward to advance the counter
+    PilParams neutral = {0.5, 0.5, 0.0, 0.0, 1.0, 0.5, 1.0, 1e-6};
+    return forward_impl(x, t, B, H, W, x_dtype, t_dtype, x_kind, &neutral, moments, nullptr, workspace, workspace_bytes, stream, true, ex);
+}
+
+int pil_sweep_finalize_xchg(const PilExchange* ex, int64_t n_global, const PilParams* params, int n_params, float* loss_out,
+                            double* moments_out, void* stream) {
+    if (!ex || !params || !loss_out) return PIL_ERR_NULL;
+    if (n_params < 1 || n_params > kSweepChunk) return PIL_ERR_SHAPE;
+    for (int k = 0; k < n_params; ++k) {
+        const int st = pil_validate_params(params + k);
+        if (st != PIL_OK) return st;
+    }
+    XchgDev X;
+    int st = make_xchg(ex, &X);
+    if (st != PIL_OK) return st;
+    if (X.device_epoch) return PIL_ERR_EXCHANGE;
+    SweepParams sp;
+    sp.n = n_params;
+    for (int k = 0; k < n_params; ++k) sp.p[k] = params[k];
+    pil_sweep_finalize_xchg_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(X, (long long)n_global, sp, loss_out, moments_out);
+    count_launch();
+    return (int)cudaGetLastError();
 }
 
 int pil_sweep_finalize(const double* moments, int64_t n_global, const PilParams* params, int n_params, float* loss_out,

@@ -464,6 +464,7 @@ struct FwdArgs {
     // from this counter (null: one static task per warp); tasks [0, first_dynamic) are the static ones
     unsigned int* task_counter;
     long long first_dynamic;
+    XchgDev X;               // MOMENTS, world > 0: the last block pushes the 16 moment sums to every rank (phases 0 and 1)
 };
 
 struct BwdArgs {

@@ -294,9 +294,10 @@ __device__ __forceinline__ void fwd_body(const FwdArgs& A, [[maybe_unused]] cons
     }
     double raw[NACC];
     if (!blocks_to_last<kThreads, NACC>(blk, A.partials, A.ticket, raw)) return;
+    [[maybe_unused]] __shared__ double s_push[MOMENTS ? 16 : 2];
     if (threadIdx.x == 0) {
         if constexpr (MOMENTS) {  // layout: include/pil.h PIL_NMOMENTS
-            double* mo = A.sums;
+            double* mo = s_push;
             mo[0] = raw[0];
             mo[1] = raw[1];
             mo[2] = raw[2];
@@ -311,6 +312,8 @@ __device__ __forceinline__ void fwd_body(const FwdArgs& A, [[maybe_unused]] cons
             mo[11] = raw[11];          // sum h*g
             mo[12] = (double)g.B * (double)g.H * (double)g.W;
             mo[13] = mo[14] = mo[15] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) A.sums[k] = mo[k];
         } else {
             double s[PIL_NSUMS];
             sums_from_raw(raw, A.p.epsilon, (double)g.B * (double)g.H * (double)g.W, s);
@@ -320,6 +323,13 @@ __device__ __forceinline__ void fwd_body(const FwdArgs& A, [[maybe_unused]] cons
         }
         if (A.task_counter != nullptr) *A.task_counter = 0u;  // every warp has made its last claim
         *A.ticket = 0u;
+    }
+    if constexpr (MOMENTS) {
+        if (A.X.world > 0) {  // data-parallel sweep: this shard's 16 sums go to every rank as two 8-double vectors
+            __syncthreads();
+            xchg_push(A.X, 0, s_push);
+            xchg_push(A.X, 1, s_push + 8);
+        }
     }
 }
 

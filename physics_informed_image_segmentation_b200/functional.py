@@ -148,19 +148,46 @@ def forward_sums(x: torch.Tensor, t: torch.Tensor, p: LossParams, kind: int, sum
     return sums, (report if finalize else None)
 
 
-def forward_moments(x: torch.Tensor, t: torch.Tensor, kind: int, moments: Optional[torch.Tensor] = None) -> torch.Tensor:
+def forward_moments(x: torch.Tensor, t: torch.Tensor, kind: int, moments: Optional[torch.Tensor] = None,
+                    ex: Optional["_lib.PilExchange"] = None) -> torch.Tensor:
     """One pass over the maps -> the 13 parameter-independent sums (float64[16]) every loss setting is a
-    closed form of (include/pil.h pil_forward_moments).  All-reduce (SUM) across ranks when sharded."""
+    closed form of (include/pil.h pil_forward_moments).  All-reduce (SUM) across ranks when sharded -- or pass `ex`
+    (a PeerExchange step descriptor): the kernel's last block then stores the shard's sums into every rank's mailbox
+    and sweep_finalize_xchg assembles the global losses without a collective call."""
     B, H, W = check_maps(x, t)
     dev = x.device
     if moments is None:
         moments = torch.empty(PIL_NMOMENTS, dtype=torch.float64, device=dev)
     ws = workspace(dev, B, H, W)
     with torch.cuda.device(dev):
-        st = _lib.lib().pil_forward_moments(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
-                                            moments.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        if ex is not None:
+            st = _lib.lib().pil_forward_moments_xchg(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                                                     moments.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(ex), _stream_ptr(dev))
+        else:
+            st = _lib.lib().pil_forward_moments(x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind,
+                                                moments.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
     _lib.check(st, "pil_forward_moments")
     return moments
+
+
+def sweep_finalize_xchg(ex: "_lib.PilExchange", n_global: int, params: Sequence[LossParams], device: torch.device,
+                        reports: Optional[torch.Tensor] = None, moments: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Loss reports (float32[K, 8], K <= 32) of the GLOBAL batch from the moment sums all ranks pushed into the mailbox
+    (forward_moments(..., ex=ex) with the same descriptor); identical on every rank."""
+    K = len(params)
+    if not (1 <= K <= 32):
+        raise ValueError("the exchanged sweep evaluates 1..32 settings per call")
+    for p in params:
+        p.validate()
+    dev = torch.device(device)
+    if reports is None:
+        reports = torch.empty(K, PIL_NOUT, dtype=torch.float32, device=dev)
+    arr = (PilParams * K)(*[p.c() for p in params])
+    with torch.cuda.device(dev):
+        st = _lib.lib().pil_sweep_finalize_xchg(ctypes.byref(ex), int(n_global), arr, K, reports.data_ptr(),
+                                                moments.data_ptr() if moments is not None else None, _stream_ptr(dev))
+    _lib.check(st, "pil_sweep_finalize_xchg")
+    return reports
 
 
 def sweep_finalize(moments: torch.Tensor, n_global: int, params: Sequence[LossParams],
@@ -186,11 +213,19 @@ def sweep_losses(x: torch.Tensor, t: torch.Tensor, params: Sequence[LossParams],
     """Batched loss evaluation of a parameter grid (reference run_ablation.py:159-224 S2/S3 grids; BASELINE
     config 4): ONE read of x and t for all K settings.  With `group`, x and t are this rank's shard of the
     batch and the moments are all-reduced, so every rank returns the losses of the global batch."""
-    moments = forward_moments(x.detach(), t.detach(), kind)
     if group is not None:
         import torch.distributed as dist
+        from .sharding import peer_exchange_for
 
+        px = peer_exchange_for(group, x.device)
+        if px is not None and not px.device_epoch and len(params) <= 32:
+            ex = px.next_step()  # the kernels swap the moment sums over peer memory: no collective call
+            forward_moments(x.detach(), t.detach(), kind, ex=ex)
+            return sweep_finalize_xchg(ex, -1, params, x.device)
+        moments = forward_moments(x.detach(), t.detach(), kind)
         dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+        return sweep_finalize(moments, -1, params)
+    moments = forward_moments(x.detach(), t.detach(), kind)
     return sweep_finalize(moments, -1, params)
 
 
