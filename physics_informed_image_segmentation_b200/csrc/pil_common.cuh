@@ -433,7 +433,13 @@ struct Geo {
     int strips;            // warps per row band = ceil(W / 120)
     long long groups;      // row ranges
     long long total_rows;  // B * H
-    long long tasks;       // groups * strips warp-tasks
+    long long tasks;       // (groups + tail_groups) * strips warp-tasks
+    // Optional tail phase (backward, dynamic claiming): rows [0, tail_rows) are cut into shorter ranges of tail_range rows
+    // -- task indices [0, tail_groups * strips) -- and only rows [tail_rows, total_rows) into the `groups` long ones.  The
+    // shard is walked from its END, so the short ranges are the LAST to be claimed: the grid finishes within a short
+    // range's length of each other instead of a long one's.  tail_rows == 0: no tail phase.
+    long long tail_rows, tail_groups;
+    int tail_range;
 };
 
 // peer-memory exchange descriptor handed to the kernels (see the exchange helpers below)
@@ -664,7 +670,7 @@ static __device__ __noinline__ bool xchg_wait_sum(const XchgDev& X, int phase, d
 // second level: the block's N doubles (thread k < N holds component k in `blk`) -> `partials` -> the LAST block to
 // finish (ticket) adds all blocks' partials in a fixed order.  Returns true in the last block only; there thread 0
 // holds the totals in out[].  The caller resets *ticket to 0 when it is done.
-template <int THREADS, int N>
+template <int THREADS, int N, int TLK = -1>
 __device__ __forceinline__ bool blocks_to_last(double blk, double* partials, unsigned int* ticket, double* out) {
     constexpr int kWarps = THREADS / 32;
     constexpr int NP = N / 2;  // component pairs (16-byte loads)
@@ -673,16 +679,19 @@ __device__ __forceinline__ bool blocks_to_last(double blk, double* partials, uns
     __shared__ double s_tot[N];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (TLK >= 0) TL_STAMP(TLK, 4);  // every warp of the block has arrived
     if (threadIdx.x < N) {
         partials[(long long)blockIdx.x * N + threadIdx.x] = blk;
         __threadfence();
     }
     __syncthreads();
+    if constexpr (TLK >= 0) TL_STAMP(TLK, 5);  // partial written and fenced
     if (threadIdx.x == 0) {
         const unsigned int done = atomicAdd(ticket, 1u);
         s_last = (done == gridDim.x - 1);
     }
     __syncthreads();
+    if constexpr (TLK >= 0) TL_STAMP(TLK, 6);  // ticket taken
     if (!s_last) return false;
     __threadfence();
     constexpr int kGroups = THREADS / NP;
@@ -735,7 +744,7 @@ __device__ __forceinline__ bool blocks_to_last(double blk, double* partials, uns
 }
 
 // first level: per-thread accumulators -> warp shuffles -> the block's doubles; then blocks_to_last
-template <int THREADS, typename AccT, int N = PIL_NSUMS>
+template <int THREADS, typename AccT, int N = PIL_NSUMS, int TLK = -1>
 __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* partials, unsigned int* ticket, double* out) {
     constexpr int kWarps = THREADS / 32;
     __shared__ double s_part[kWarps][N];
@@ -753,7 +762,7 @@ __device__ __forceinline__ bool reduce_to_last_block(const AccT* acc, double* pa
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) blk += s_part[w][threadIdx.x];
     }
-    return blocks_to_last<THREADS, N>(blk, partials, ticket, out);
+    return blocks_to_last<THREADS, N, TLK>(blk, partials, ticket, out);
 }
 
 // raw accumulator totals -> the sums vector of include/pil.h
@@ -845,6 +854,8 @@ inline Geo make_geo(int64_t B, int64_t H, int64_t W, int resident_blocks, int fo
     g.W = (int)W;
     g.strips = (int)((W + kStripCols - 1) / kStripCols);
     g.total_rows = (long long)B * H;
+    g.tail_rows = g.tail_groups = 0;
+    g.tail_range = 0;
     long long groups;
     if (forced_rows > 0) {
         groups = (g.total_rows + forced_rows - 1) / forced_rows;
@@ -911,6 +922,11 @@ inline cudaError_t launch_pdl(K kernel, int blocks, int threads, int smem, cudaS
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+template <typename T>
+constexpr int dtype_code() {
+    return std::is_same<T, float>::value ? PIL_F32 : (std::is_same<T, __nv_bfloat16>::value ? PIL_BF16 : PIL_U8);
 }
 
 // 2-D tensor map of a (rows x cols) row-major map with a (box_rows x box_cols) box; false when the layout does not

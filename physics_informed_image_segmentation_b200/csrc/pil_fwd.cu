@@ -367,10 +367,6 @@ static bool fwd_want_tma() {
     }
     return env == 1;
 }
-template <typename T>
-constexpr int dtype_code() {
-    return std::is_same<T, float>::value ? PIL_F32 : (std::is_same<T, __nv_bfloat16>::value ? PIL_BF16 : PIL_U8);
-}
 
 template <int KIND, typename XT, typename TT>
 static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, bool aligned, size_t partial_bytes_avail,

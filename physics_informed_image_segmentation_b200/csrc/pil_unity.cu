@@ -5,3 +5,4 @@
 #include "pil_point.cu"
 #include "pil_bwd.cu"
 #include "pil_api.cu"
+#include "pil_tail.cu"

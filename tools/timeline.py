@@ -65,6 +65,11 @@ for ker in range(2):
     ent, wait, loop, ex = X[:, 0], X[:, 1], X[:, 2], X[:, 3]
     print(f"  {names[ker]:14s} entry {ent.min():7.1f}..{ent.max():7.1f} | after wait {wait.min():7.1f}..{wait.max():7.1f} | "
           f"loop end {loop.min():7.1f}..{loop.max():7.1f} (p50 {np.median(loop):7.1f}, p95 {np.percentile(loop, 95):7.1f}) | exit max {ex.max():7.1f}")
+    if ker == 1 and X.shape[0] and T[k, ker, :nb[ker], 4].max() > 0:
+        Y = (T[k, ker, :nb[ker], 4:7] - t0) / 1e3
+        print(f"      epilogue: all warps of the block arrived {Y[:, 0].min():7.1f}..{Y[:, 0].max():7.1f} | partial written + fenced "
+              f"+{np.median(Y[:, 1] - Y[:, 0]):.2f} (max +{(Y[:, 1] - Y[:, 0]).max():.2f}) | ticket +{np.median(Y[:, 2] - Y[:, 1]):.2f} "
+              f"(max +{(Y[:, 2] - Y[:, 1]).max():.2f}) | last block: ticket at {Y[:, 2].max():7.1f}, exit {ex.max():7.1f}")
     smid = T[k, ker, :nb[ker], 7]
     dur = loop - wait
     print(f"      main-loop duration per block: min {dur.min():.1f} p50 {np.median(dur):.1f} p95 {np.percentile(dur, 95):.1f} max {dur.max():.1f} us; "
