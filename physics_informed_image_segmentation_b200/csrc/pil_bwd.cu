@@ -87,14 +87,16 @@ static __device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const double*
 template <int KIND, typename XT, typename TT, bool ALIGNED, bool TMA>
 __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] const CUtensorMap* tmx, [[maybe_unused]] const CUtensorMap* tmt) {
     static_assert(ALIGNED || !TMA, "the TMA stage ring needs the aligned layout");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction: TMA operands live in uniform registers
     [[maybe_unused]] unsigned int tma_q = 0;  // TMA: boxes this warp has consumed so far (stage = q & 1, phase = (q >> 1) & 1)
     if constexpr (TMA) {
         extern __shared__ __align__(128) unsigned char smem_tma[];
         if (threadIdx.x == 0) {
-            const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem_tma + TmaRing<XT, TT>::kBarOffset);
+            using Ring0 = TmaRing<XT, TT>;
+            const uint32_t base0 = (uint32_t)__cvta_generic_to_shared(smem_tma);
 #pragma unroll
-            for (int q = 0; q < 2 * kWarpsPerBlock; ++q) mbar_init(bars + 8 * q, 1);
+            for (int q = 0; q < 2 * kWarpsPerBlock; ++q) mbar_init(base0 + (q >> 1) * Ring0::kWarpBytes + Ring0::kWarpBarOffset + 8 * (q & 1), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
@@ -500,8 +502,8 @@ __device__ __forceinline__ void bwd_body(const BwdArgs& A, [[maybe_unused]] cons
         // the shard) are zero-filled by the TMA unit and never used; the mirror fix-up stays at consume time.
         using Ring = TmaRing<XT, TT>;
         extern __shared__ __align__(128) unsigned char smem_tma[];
-        const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(smem_tma) + warp * 2 * Ring::kStageBytes;
-        const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(smem_tma) + Ring::kBarOffset + 16 * warp;
+        const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(smem_tma) + warp * Ring::kWarpBytes;  // this warp's two stages ...
+        const uint32_t bar_s = wbase_s + Ring::kWarpBarOffset;                                                // ... and their two mbarriers
         const int c0 = strip * kStripCols - kVec;  // first column of the warp's 128-column window
         const int cbx = TmaBox<XT>::first_col(c0), cbt = TmaBox<TT>::first_col(c0);  // first columns of the (16-byte aligned) boxes
         const int xoff = (cx.colc - cbx) * (int)sizeof(XT), toff = (cx.colc - cbt) * (int)sizeof(TT) + Ring::kXSlotBytes;
@@ -791,7 +793,7 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
             make_tensor_map_2d(&tmx, a.x, dtype_code<XT>(), (long long)B * H, W, Ring::kBoxRows, TmaBox<XT>::kCols) &&
             make_tensor_map_2d(&tmt, a.t, dtype_code<TT>(), (long long)B * H, W, Ring::kBoxRows, TmaBox<TT>::kCols)) {
             out->tma = 1;
-            return go(pil_bwd_kernel_tma<KIND, XT, TT>, Ring::kSmemBytes, 2, tmx, tmt);
+            return go(pil_bwd_kernel_tma<KIND, XT, TT>, Ring::kSmemBytesB, 2, tmx, tmt);
         }
         return go(pil_bwd_kernel<KIND, XT, TT, true>, kSmemPerBlock, 1);
     }

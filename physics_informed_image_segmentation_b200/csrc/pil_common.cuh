@@ -312,8 +312,12 @@ struct TmaRing {
     static constexpr int kXBoxBytes = kBoxRows * kXRowBytes, kTBoxBytes = kBoxRows * kTRowBytes;  // what the TMA unit delivers
     static constexpr int kXSlotBytes = (kXBoxBytes + 127) / 128 * 128, kTSlotBytes = (kTBoxBytes + 127) / 128 * 128;
     static constexpr int kStageBytes = kXSlotBytes + kTSlotBytes;  // every box starts 128-byte aligned
-    static constexpr int kBarOffset = kWarpsPerBlock * 2 * kStageBytes;
+    static constexpr int kBarOffset = kWarpsPerBlock * 2 * kStageBytes;   // layout A: all stages, then all mbarriers (forward kernel)
     static constexpr int kSmemBytes = kBarOffset + kWarpsPerBlock * 2 * 8;
+    // layout B (backward kernel): per warp {stage 0, stage 1, 2 mbarriers, pad to 128}: one base register reaches everything
+    static constexpr int kWarpBarOffset = 2 * kStageBytes;
+    static constexpr int kWarpBytes = 2 * kStageBytes + 128;
+    static constexpr int kSmemBytesB = kWarpsPerBlock * kWarpBytes;
 };
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

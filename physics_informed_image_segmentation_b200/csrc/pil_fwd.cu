@@ -20,7 +20,8 @@ constexpr int kFwdTmaDefault = 1;  // staging of the aligned full-forward kernel
 template <int KIND, typename XT, typename TT, bool ALIGNED, bool MOMENTS, bool TMA>
 __device__ __forceinline__ void fwd_body(const FwdArgs& A, [[maybe_unused]] const CUtensorMap* tmx, [[maybe_unused]] const CUtensorMap* tmt) {
     static_assert(ALIGNED || !TMA, "the TMA stage ring needs the aligned layout");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction (TMA operands, task bookkeeping)
     const Geo& g = A.g;
     constexpr int NACC = MOMENTS ? 16 : 8;
     using Ring = TmaRing<XT, TT, 3>;
