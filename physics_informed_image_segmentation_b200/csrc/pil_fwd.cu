@@ -20,8 +20,8 @@ constexpr int kFwdTmaDefault = 1;  // staging of the aligned full-forward kernel
 template <int KIND, typename XT, typename TT, bool ALIGNED, bool MOMENTS, bool TMA>
 __device__ __forceinline__ void fwd_body(const FwdArgs& A, [[maybe_unused]] const CUtensorMap* tmx, [[maybe_unused]] const CUtensorMap* tmt) {
     static_assert(ALIGNED || !TMA, "the TMA stage ring needs the aligned layout");
-    const int lane = threadIdx.x & 31;
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction (TMA operands, task bookkeeping)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // (a shuffled, provably uniform warp index helps K2 but makes ptxas
+                                                                 // drop this kernel's 3-row steady loop: 117 -> 138 us)
     const Geo& g = A.g;
     constexpr int NACC = MOMENTS ? 16 : 8;
     using Ring = TmaRing<XT, TT, 3>;
@@ -356,7 +356,7 @@ static int fwd_dynamic_rows(long long total_rows, long long strips, long long re
     if (forced >= 0) return (forced > 0 && forced < kMinRows) ? kMinRows : forced;
     const int rows = 64;
     const double waves = (double)(((total_rows + rows - 1) / rows) * strips) / (double)resident_warps;
-    return waves < 2.5 ? 0 : rows;
+    return waves < 2.0 ? 0 : rows;  // 7 blocks per SM: 64x1024^2 is 2.2 waves, measured faster dynamic (111.8 against 116.9 us)
 }
 static bool fwd_want_tma() {
     const int forced = host_state().bwd_stage.load();  // pil_set_bwd_staging covers both stencil kernels
