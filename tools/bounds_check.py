@@ -1,9 +1,12 @@
 """Memory-safety check of the fused kernels with a -DPIL_BOUNDS build (every global read / cp.async source /
 store is checked against the extents of the call's tensors; compute-sanitizer is not available on the pool):
 
-    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared -DPIL_BOUNDS -DPIL_DEV_F32_ONLY \
-         -I include -o build/libpil_bounds.so physics_informed_image_segmentation_b200/csrc/*.cu
-    PIL_LIB=build/libpil_bounds.so python tools/bounds_check.py
+    cd physics_informed_image_segmentation_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC \
+         -shared -DPIL_BOUNDS -DPIL_DEV_F32_ONLY -I ../../include -I . -o dev/libpil_bounds.so pil_unity.cu pil_session.cu \
+         pil_graph.cu pil_boundary.cu
+    PIL_LIB=physics_informed_image_segmentation_b200/csrc/dev/libpil_bounds.so python tools/bounds_check.py
+    (add PIL_BWD_STAGE=cpasync PIL_FWD_STAGE=cpasync for the cp.async ring; the TMA boxes are bounds-safe by construction --
+    the TMA unit zero-fills what lies outside the tensor map -- and their direct loads, stores and results are checked)
 
 The tensors are carved out of the MIDDLE of a larger allocation, so an access that strays outside them lands in
 poisoned (NaN) memory of the same allocation instead of faulting -- it is counted, and would also corrupt the sums."""
