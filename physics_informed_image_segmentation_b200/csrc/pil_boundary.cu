@@ -52,23 +52,41 @@ struct BArgs {
 };
 
 // threshold both maps (src/evaluate.py:146 `predictions > threshold`; extract_boundaries :113 casts mask*255 to uint8 and
-// findContours treats non-zero as foreground) and initialise the union-find forests
+// findContours treats non-zero as foreground) and initialise the union-find forests.  A warp covers 32 consecutive pixels;
+// a background pixel starts out labelled with the FIRST pixel of its horizontal run inside the warp's chunk (one ballot),
+// so long runs arrive pre-merged and the merge kernel only has to stitch chunk boundaries and vertically adjacent runs.
 __global__ void __launch_bounds__(kThreads) bf1_init(const BArgs A) {
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < A.n; i += (long long)gridDim.x * kThreads) {
-        float u = load_f(A.x, A.x_dtype, i);
-        if (A.x_kind != PIL_X_PROB) {
-            const float s = (A.x_kind == PIL_X_LOGITS_TANH) ? 2.0f : 1.0f;
-            u = 1.0f / (1.0f + expf(-s * u));  // src/unet.py:208-214
+    const int lane = threadIdx.x & 31;
+    const long long n32 = (A.n + 31) / 32 * 32;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n32; i += (long long)gridDim.x * kThreads) {
+        const bool valid = i < A.n;
+        bool fp = true, ft = true;
+        int col = 0;
+        if (valid) {
+            float u = load_f(A.x, A.x_dtype, i);
+            if (A.x_kind != PIL_X_PROB) {
+                const float s = (A.x_kind == PIL_X_LOGITS_TANH) ? 2.0f : 1.0f;
+                u = 1.0f / (1.0f + expf(-s * u));  // src/unet.py:208-214
+            }
+            fp = u > A.threshold;
+            const float tv = load_f(A.t, A.t_dtype, i) * 255.0f;
+            ft = ((unsigned char)(int)tv) != 0;  // (mask * 255).astype(np.uint8) != 0
+            col = (int)(i % A.W);
         }
-        const bool fp = u > A.threshold;
-        const float tv = load_f(A.t, A.t_dtype, i) * 255.0f;
-        const bool ft = ((unsigned char)(int)tv) != 0;  // (mask * 255).astype(np.uint8) != 0
-        A.fg[i] = (unsigned char)((fp ? 1 : 0) | (ft ? 2 : 0));
-        A.label[i] = fp ? -1 : (int)i;
-        A.label[A.n + i] = ft ? -1 : (int)i;
-        A.outside[i] = 0;
-        A.outside[A.n + i] = 0;
-        A.bnd[i] = 0;
+        // "continues the run of the pixel to its left" (same row, same warp chunk), per plane
+        const unsigned bgp = __ballot_sync(0xffffffffu, valid && !fp), bgt = __ballot_sync(0xffffffffu, valid && !ft);
+        const unsigned row_start = __ballot_sync(0xffffffffu, col == 0);
+        const unsigned contp = bgp & (bgp << 1) & ~row_start, contt = bgt & (bgt << 1) & ~row_start;
+        if (valid) {
+            // number of consecutive "continues" bits ending at this lane = distance to the run's first pixel in the chunk
+            const int kp = __clz(~(contp << (31 - lane))), kt = __clz(~(contt << (31 - lane)));
+            A.fg[i] = (unsigned char)((fp ? 1 : 0) | (ft ? 2 : 0));
+            A.label[i] = fp ? -1 : (int)(i - kp);
+            A.label[A.n + i] = ft ? -1 : (int)(i - kt);
+            A.outside[i] = 0;
+            A.outside[A.n + i] = 0;
+            A.bnd[i] = 0;
+        }
     }
 }
 
@@ -97,7 +115,9 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     }
 }
 
-// background 4-connectivity inside every image: merge with the left and the upper neighbour
+// background 4-connectivity inside every image.  Runs are pre-merged inside 32-pixel chunks (bf1_init), so a pixel only
+// merges with its LEFT neighbour across a chunk boundary, and with its UPPER neighbour where the pair (pixel, upper pixel)
+// does not simply continue the pair to its left -- one union per pair of vertically touching runs instead of one per pixel.
 __global__ void __launch_bounds__(kThreads) bf1_merge(const BArgs A) {
     const long long total = 2 * A.n;
     for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < total; q += (long long)gridDim.x * kThreads) {
@@ -107,8 +127,12 @@ __global__ void __launch_bounds__(kThreads) bf1_merge(const BArgs A) {
         if (L[i] < 0) continue;
         const int col = (int)(i % A.W);
         const int row = (int)((i / A.W) % A.H);
-        if (col > 0 && L[i - 1] >= 0) uf_union(L, (int)i, (int)(i - 1));
-        if (row > 0 && L[i - A.W] >= 0) uf_union(L, (int)i, (int)(i - A.W));
+        const bool left = col > 0 && L[i - 1] >= 0;
+        if (left && (i & 31) == 0) uf_union(L, (int)i, (int)(i - 1));
+        if (row > 0 && L[i - A.W] >= 0) {
+            const bool same_pair_as_left = left && L[i - A.W - 1] >= 0;
+            if (!same_pair_as_left) uf_union(L, (int)i, (int)(i - A.W));
+        }
     }
 }
 
