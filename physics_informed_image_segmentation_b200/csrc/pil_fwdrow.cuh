@@ -89,9 +89,11 @@ struct FwdRow {
     // stencil2(): residual and gradient-energy terms of a pixel pair of the centre row.
     //   r = D*(s4 - 4u) + u(1-u)(u-a) as a polynomial in u: u*(u*((1+a) - u) - a - 4D) + D*s4
     float a1, c0;  // 1+a, -a-4D
-    __device__ __forceinline__ void stencil2(f2 u, f2 lf, f2 rt, f2 m, f2 p) {
-        const f2 s4 = add2(add2(lf, rt), add2(m, p));                                       // src/pde.py:73-77
-        const f2 dx = sub2(rt, lf), dy = sub2(p, m);                                        // 2*gx, 2*gy (src/pde.py:172-173)
+    // hs = left + right neighbour, dx = right - left neighbour of the pair (both formed with SCALAR adds on the six values
+    // {L, s0..s3, R} by the caller: packing the misaligned pairs (L,s0) (s1,s2) (s3,R) would cost register moves)
+    __device__ __forceinline__ void stencil2(f2 u, f2 hs, f2 dx, f2 m, f2 p) {
+        const f2 s4 = add2(hs, add2(m, p));                                                 // src/pde.py:73-77
+        const f2 dy = sub2(p, m);                                                           // 2*gy (src/pde.py:173); dx = 2*gx (:172)
         if constexpr (MOMENTS) {
             const f2 lap = fma2(bc(-4.0f), u, s4);
             const f2 gq = mul2(u, sub2(bc(1.0f), u)), hq = mul2(gq, u);
@@ -110,9 +112,10 @@ struct FwdRow {
     __device__ __forceinline__ void stencil4(const float4& um, const float4& uc, const float4& up) {
         const float L = __shfl_up_sync(0xffffffffu, uc.w, 1);
         const float R = __shfl_down_sync(0xffffffffu, uc.x, 1);
-        const f2 A = make_float2(L, uc.x), B = make_float2(uc.y, uc.z), C = make_float2(uc.w, R);
-        stencil2(make_float2(uc.x, uc.y), A, B, make_float2(um.x, um.y), make_float2(up.x, up.y));
-        stencil2(make_float2(uc.z, uc.w), B, C, make_float2(um.z, um.w), make_float2(up.z, up.w));
+        const f2 hs0 = make_float2(L + uc.y, uc.x + uc.z), hs1 = make_float2(uc.y + uc.w, uc.z + R);
+        const f2 dx0 = make_float2(uc.y - L, uc.z - uc.x), dx1 = make_float2(uc.w - uc.y, R - uc.z);
+        stencil2(make_float2(uc.x, uc.y), hs0, dx0, make_float2(um.x, um.y), make_float2(up.x, up.y));
+        stencil2(make_float2(uc.z, uc.w), hs1, dx1, make_float2(um.z, um.w), make_float2(up.z, up.w));
     }
 
     __device__ __forceinline__ void row(const float4& um, const float4& uc, const float4& up, const float4& tt) {

@@ -90,3 +90,18 @@ def test_pointwise_forward_uses_three_mufu_per_pixel():
     rcp = sum(1 for t in text if re.search(r"MUFU\.RCP\b", t))   # not the fp64 RCP64H of the finalisation
     lg2 = sum(1 for t in text if "MUFU.LG2" in t)
     assert ex2 == rcp == lg2 and ex2 > 0, (ex2, rcp, lg2)  # den = 1 + 2^xs, u = 1/den, L = lg2(den): 3 MUFU per pixel
+
+
+def test_unity_development_build_compiles(tmp_path):
+    """csrc/pil_unity.cu is the single-translation-unit form the instrumented development builds use (-DPIL_TIMELINE for
+    tools/timeline.py, -DPIL_BOUNDS for tools/bounds_check.py): it must keep compiling as the pieces evolve."""
+    import os
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    out = tmp_path / "unity.o"
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-DPIL_BOUNDS", "-DPIL_TIMELINE",
+           "-DPIL_DEV_F32_ONLY", "-I", _lib.INCLUDE, "-I", _lib.CSRC, "-c", "-o", str(out), os.path.join(_lib.CSRC, "pil_unity.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]

@@ -72,6 +72,12 @@ __global__ void bench(float* out, unsigned long long* cyc, float k0, float k1, f
                              " fma.rn.f32x2 rc, ra, rb, rc; mov.b64 {%0, %1}, rc;}"
                              : "+f"(C[i].x), "+f"(C[i].y) : "f"(A[i].x), "f"(A[i].y), "f"(B[i].x), "f"(B[i].y));
                 if (i % 4 == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(c[i]));
+            } else if constexpr (MODE >= 20 && MODE <= 23) {  // FFMA2 (broadcast form, 2 pipe cycles) + MUFU.EX2 on 1/8, 1/4, 1/2, 1/1 of them
+                asm volatile("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %4}; mov.b64 rc, {%0, %1};"
+                             " fma.rn.f32x2 rc, ra, rb, rc; mov.b64 {%0, %1}, rc;}"
+                             : "+f"(C[i].x), "+f"(C[i].y) : "f"(A[i].x), "f"(A[i].y), "f"(k0));
+                constexpr int every = MODE == 20 ? 8 : (MODE == 21 ? 4 : (MODE == 22 ? 2 : 1));
+                if (i % every == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(c[i]));
             } else if constexpr (MODE == 13) {  // alternating FFMA (const operand) and integer IADD3 (alu pipe)
                 asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(c[i]) : "f"(a[i]), "f"(k0));
                 asm volatile("add.u32 %0, %0, %1;" : "+r"(H[i]) : "r"(HB[i]));
@@ -125,6 +131,11 @@ int main() {
     run<8>("MUFU.EX2", 1, out, cyc, sms);
     run<12>("FFMA2 + 1/4 MUFU.EX2 (per FFMA2)", 1, out, cyc, sms);
     run<13>("FFMA c[] + IADD (per pair)", 1, out, cyc, sms);
+    // do the FMA and XU pipes overlap?  cycles per FFMA2 (2.0 alone); the MUFU share alone would cost 1.0 / 2.0 / 4.0 / 8.0
+    run<20>("FFMA2 bcast + 1/8 MUFU.EX2 (per FFMA2)", 1, out, cyc, sms);
+    run<21>("FFMA2 bcast + 1/4 MUFU.EX2 (per FFMA2)", 1, out, cyc, sms);
+    run<22>("FFMA2 bcast + 1/2 MUFU.EX2 (per FFMA2)", 1, out, cyc, sms);
+    run<23>("FFMA2 bcast + 1/1 MUFU.EX2 (per FFMA2)", 1, out, cyc, sms);
     cudaError_t e = cudaGetLastError();
     printf("status: %s\n", cudaGetErrorString(e));
     return e == cudaSuccess ? 0 : 1;
