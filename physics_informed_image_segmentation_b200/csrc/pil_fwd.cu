@@ -7,6 +7,7 @@
 
 namespace pil {
 
+constexpr int kMomentsMode = 0;    // MOMENTS instantiation: static ranges + cp.async ring (A/B in DESIGN.md)
 constexpr int kFwdTmaDefault = 1;  // staging of the aligned full-forward kernel when nothing is forced (A/B in DESIGN.md)
 
 // One warp = one 120-column strip of a range of rows (see pil_common.cuh); after its first, statically assigned
@@ -380,7 +381,12 @@ static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, boo
         const long long strips_ = (W + kStripCols - 1) / kStripCols;
         // measured on B200 at 64x1024^2: the sums kernel gains 8% from TMA boxes + dynamic ranges; the MOMENTS
         // instantiation (16 accumulators to fold per task, 6 blocks per SM) is faster with one static range per warp
-        const int dyn_rows = (tune_rps > 0 || moments) ? 0 : fwd_dynamic_rows(B * H, strips_, (long long)resident * kWarpsPerBlock);
+        static int mom_mode = -1;  // PIL_MOM_MODE: bit 0 = dynamic ranges, bit 1 = TMA boxes for the MOMENTS instantiation (experiments)
+        if (mom_mode < 0) {
+            const char* e = getenv("PIL_MOM_MODE");
+            mom_mode = e ? atoi(e) : kMomentsMode;
+        }
+        const int dyn_rows = (tune_rps > 0 || (moments && !(mom_mode & 1))) ? 0 : fwd_dynamic_rows(B * H, strips_, (long long)resident * kWarpsPerBlock);
         if (dyn_rows > 0 && out->task_counter != nullptr) {
             a.g = make_geo(B, H, W, resident, dyn_rows, 1);
             const long long need = (a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -404,10 +410,16 @@ static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, boo
     if (aligned) {
         using Ring = TmaRing<XT, TT, 3>;
         CUtensorMap tmx, tmt;
-        if (fwd_want_tma() && !moments &&
+        static int mom_mode2 = -1;
+        if (mom_mode2 < 0) {
+            const char* e = getenv("PIL_MOM_MODE");
+            mom_mode2 = e ? atoi(e) : kMomentsMode;
+        }
+        if (fwd_want_tma() && (!moments || (mom_mode2 & 2)) &&
             make_tensor_map_2d(&tmx, a.x, dtype_code<XT>(), (long long)B * H, W, Ring::kBoxRows, TmaBox<XT>::kCols) &&
             make_tensor_map_2d(&tmt, a.t, dtype_code<TT>(), (long long)B * H, W, Ring::kBoxRows, TmaBox<TT>::kCols)) {
             out->tma = 1;
+            if (moments) return go(pil_fwd_kernel_tma<KIND, XT, TT, true>, Ring::kSmemBytes, 2, tmx, tmt);
             return go(pil_fwd_kernel_tma<KIND, XT, TT, false>, Ring::kSmemBytes, 2, tmx, tmt);
         }
         if (moments) return go(pil_fwd_kernel<KIND, XT, TT, true, true>, kSmemPerBlock, 1);

@@ -103,6 +103,20 @@ class PeerExchange:
         self._epoch += 1  # device-epoch mode: informational only, the kernels count the steps themselves
         return ex
 
+    def check_lockstep(self) -> None:
+        """Collective, one small all-reduce: every rank must have taken the same number of exchange steps.  The step tag
+        comes from this host-side counter (host-epoch mode), so one extra or missing grad-mode forward on one rank
+        desynchronises every later step -- the kernels then time out (NaN loss, zero gradient, `timed_out()`).  Call it
+        where a host sync happens anyway; training.train_epoch does at the end of every epoch."""
+        import torch.distributed as dist
+
+        e = torch.tensor([self._epoch, -self._epoch], dtype=torch.int64, device=self.device)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX, group=self.group)
+        lo, hi = -int(e[1].item()), int(e[0].item())
+        if lo != hi:
+            raise RuntimeError(f"peer exchange out of lock step: ranks have taken between {lo} and {hi} exchange steps "
+                               f"(this rank: {self._epoch}); every rank must evaluate the loss the same number of times")
+
     def timed_out(self) -> bool:
         """Host sync: has any exchange wait on this rank given up (peer dead / not in lock step)?"""
         import ctypes

@@ -90,6 +90,8 @@ def _results(criterion, acc: _EpochAccumulator, return_components: bool, compute
         from .sharding import peer_exchange_for
 
         px = peer_exchange_for(group, vec.device)
+        if px is not None:
+            px.check_lockstep()
         if px is not None and px.timed_out():
             raise RuntimeError("a peer-memory exchange wait timed out during this epoch: a rank died or the ranks are not "
                                "evaluating the loss in lock step (PIL_XCHG_TIMEOUT_MS)")
