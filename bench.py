@@ -171,7 +171,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "strong" if (args.gpus > 1 and args.scaling != "weak") else "weak",
+        "scaling": "weak" if args.scaling == "weak" else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}_fp32", "stage2_params": STAGE2, "entry": "sigmoid -> loss -> backward on CPU"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -504,7 +504,8 @@ def run_loss(args, C: Ctx):
     dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     esz = 4 if args.dtype == "f32" else 2
     wl_name = f"{name}_{'fp32' if args.dtype == 'f32' else 'bf16'}"
-    scaling = "weak" if (not C.distributed or args.scaling == "weak") else "strong"
+    # the default series (N = 1, 2, 4, 8 on the same GLOBAL batch) is a strong-scaling series; at N = 1 both modes coincide
+    scaling = "weak" if args.scaling == "weak" else "strong"
     X = Exchanges(C, args.exchange)
 
     sampler = ClockSampler(C.local_rank)

@@ -283,6 +283,51 @@ def test_full_size_shard_additivity_and_determinism(Fn, po, dev):
         assert rel_scalar(gs[k].item(), osums[k]) < TOL
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_full_size_cfg5_training_step_properties(Fn, po, dev, dtype):
+    """128 x 2048 x 2048 (BASELINE config 5), fp32 and bf16 maps, through the TRAINING-step kernels (pointwise forward +
+    accumulating backward): (a) shard sums add up to the batch sums, (b) the backward of a shard given the global sums is
+    the batch backward restricted to the shard, bit for bit (a pixel's gradient does not depend on how the rows were
+    partitioned), (c) the first and the last image against the fp64 oracle given the global sums, (d) the loss report
+    against the oracle's finalize of those sums, (e) the loss is linear in its weights."""
+    B, H, W = 128, 2048, 2048
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 16 * (1 << 30):
+        pytest.skip("needs 16 GB of free device memory")
+    g = torch.Generator(device=dev).manual_seed(91)
+    z = torch.empty(B, 1, H, W, dtype=dtype, device=dev)
+    t = torch.empty(B, 1, H, W, dtype=dtype, device=dev)
+    for b in range(0, B, 16):  # generated in slices: no 2 GB fp32 temporaries for the bf16 case
+        z[b:b + 16] = (2.0 * torch.randn(16, 1, H, W, device=dev, generator=g)).to(dtype)
+        t[b:b + 16] = (torch.rand(16, 1, H, W, device=dev, generator=g) > 0.5).to(dtype)
+    p = lp(Fn, po.STAGE2)
+    n = z.numel()
+    rep, sums, grad = Fn.loss_fwd_bwd(z, t, p, 1)
+    bounds = ((0, 16), (16, 80), (80, 128))
+    parts = [Fn.forward_pointwise(z[a:b], t[a:b], p, 1).clone() for a, b in bounds]
+    ptot = parts[0] + parts[1] + parts[2]
+    full_point = Fn.forward_pointwise(z, t, p, 1)
+    assert torch.allclose(ptot[:4], full_point[:4], rtol=1e-6, atol=0) and ptot[7] == full_point[7] == n
+    stencil_tot = torch.zeros(8, dtype=torch.float64, device=dev)
+    for a, b in bounds:
+        g_part, st = Fn.backward_accumulate(z[a:b], t[a:b], p, 1, full_point, n)
+        assert torch.equal(g_part, grad[a:b]), (a, b)
+        stencil_tot += st
+    assert torch.allclose((full_point + stencil_tot)[:6], sums[:6], rtol=1e-6, atol=0)
+    tol = TOL if dtype == torch.float32 else 1e-2
+    gs = sums.cpu().numpy()
+    for b in (0, B - 1):
+        zs, ts = z[b:b + 1].float().cpu().numpy().astype(np.float64), t[b:b + 1].float().cpu().numpy().astype(np.float64)
+        og = po.backward(zs, ts, po.STAGE2, gs, n, 1)
+        assert rel_max(grad[b:b + 1].float().cpu().numpy(), og) < tol, b
+    comps = po.finalize(gs, n, po.STAGE2)
+    r = rep.double().cpu().numpy()
+    for k in range(5):
+        assert rel_scalar(r[k], comps[k]) < 1e-6, k
+    pp = po.STAGE2
+    assert rel_scalar(r[0], pp.dice_weight * r[1] + pp.bce_weight * r[2] + pp.pde_weight * r[3] + pp.phase_field_weight * r[4]) < 1e-6
+
+
 def test_forced_segment_lengths_agree(Fn, po, dev):
     """the tiling is an implementation detail: every rows-per-segment choice gives the same answer"""
     from physics_informed_image_segmentation_b200 import _lib
