@@ -90,9 +90,10 @@ const char* pil_status_string(int status);
 /* Constructor-time and call-time validation of the reference (src/pde.py:14-17, :199-200). */
 int pil_validate_params(const PilParams* p);
 
-/* Scratch the forward kernel needs for its deterministic two-level reduction.  The caller owns it,
- * must zero it once (pil_workspace_init or cudaMemset) and may reuse it call after call on the same
- * stream; the kernel leaves it zeroed where it must be. */
+/* Scratch the kernels need for their deterministic two-level reductions.  The caller owns it, must zero ALL of
+ * it once (pil_workspace_init, or cudaMemset over pil_workspace_bytes) and may reuse it call after call on the same
+ * stream; the kernels leave it ready for the next launch.  (The per-block partial sums are validated by a per-launch
+ * tag instead of a memory fence, so stale bytes must not look like a tag: hence the zero.) */
 size_t pil_workspace_bytes(int64_t B, int64_t H, int64_t W);
 int pil_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 

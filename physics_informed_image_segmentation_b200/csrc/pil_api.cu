@@ -309,7 +309,7 @@ static WorkspaceLayout workspace_layout(int64_t B, int64_t H, int64_t W) {
     l.ticket_off = 0;
     l.scratch_off = 64;   // PIL_NSUMS doubles of scratch (pil_loss_fwd_bwd)
     l.partials_off = 256;
-    l.total = l.partials_off + (size_t)(blocks > kMaxPointBlocks ? blocks : kMaxPointBlocks) * PIL_NMOMENTS * sizeof(double);
+    l.total = l.partials_off + (size_t)(blocks > kMaxPointBlocks ? blocks : kMaxPointBlocks) * PIL_NMOMENTS * kPartialBytes;
     return l;
 }
 }  // namespace pil
@@ -356,7 +356,9 @@ size_t pil_workspace_bytes(int64_t B, int64_t H, int64_t W) {
 int pil_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
     if (!workspace) return PIL_ERR_NULL;
     if (workspace_bytes < 256) return PIL_ERR_WORKSPACE;
-    return (int)cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream);
+    // header AND partials: a partial slot is valid when it carries the tag of the current launch (pil_common.cuh), so no
+    // slot may start out with bytes that could pass for one
+    return (int)cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream);
 }
 
 static int forward_impl(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,

@@ -38,26 +38,33 @@ struct BwdCoef {
 // if asked, assembles the loss from (global pointwise sums + these) -- src/loss.py:144-160.
 // acc2 = {sum r^2, sum dx^2+dy^2} of this thread: the only two sums the backward produces, so the cross-block
 // reduction moves 16 bytes per block instead of 64 (it is serial time at the very end of the kernel).
-static __device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const double* acc2, const double* gs) {
+static __device__ __forceinline__ void bwd_epilogue(const BwdArgs& A, const double* acc2, const double* gs) {
+    // the global pointwise sums the loss is assembled from: requested now (threads 0..7), used after the reduction's
+    // L2 round trips instead of adding one more to the serial tail of the kernel
+    const bool wants_total = A.loss_out != nullptr || A.total_sums != nullptr;
+    double g_k = 0.0;
+    if (threadIdx.x < PIL_NSUMS && wants_total) g_k = gs[threadIdx.x];
     double raw2[2];
     if (!reduce_to_last_block<kThreads, double, 2, 1>(acc2, A.partials, A.ticket, raw2)) return;
-    const double raw[PIL_NSUMS] = {0.0, 0.0, 0.0, 0.0, raw2[0], raw2[1], 0.0, 0.0};
     __shared__ double s_push[PIL_NSUMS];   // this shard's stencil sums
     __shared__ double s_glob[PIL_NSUMS];   // the global stencil sums
+    __shared__ double s_tot[PIL_NSUMS];    // global pointwise + stencil sums
+    __shared__ double s_term[PIL_NSUMS];   // loss terms (finalize_term)
     if (threadIdx.x == 0) {
         double sb[PIL_NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        sb[4] = raw[4];
-        sb[5] = (A.p.epsilon / 8.0) * raw[5];
+        sb[4] = raw2[0];
+        sb[5] = (A.p.epsilon / 8.0) * raw2[1];
 #pragma unroll
         for (int k = 0; k < PIL_NSUMS; ++k) {
             A.stencil_sums[k] = sb[k];
             s_push[k] = sb[k];
             s_glob[k] = sb[k];
         }
+        if (A.task_counter != nullptr) *A.task_counter = 0u;  // every warp has made its last claim
     }
+    __syncthreads();
     bool finalize = true;
     if (A.X.world > 0) {  // data parallel: swap the stencil sums with every rank, then finalise globally
-        __syncthreads();
         xchg_push(A.X, 1, s_push);
         if (A.X.defer) {
             finalize = false;
@@ -65,21 +72,24 @@ static __device__ __noinline__ void bwd_epilogue(const BwdArgs& A, const double*
             xchg_wait_sum(A.X, 1, s_glob);
         }
     }
-    if (threadIdx.x == 0) {
-        if ((A.loss_out != nullptr || A.total_sums != nullptr) && finalize) {
-            double tot[PIL_NSUMS];
-#pragma unroll
-            for (int k = 0; k < PIL_NSUMS; ++k) tot[k] = gs[k] + s_glob[k];
-            if (A.loss_out != nullptr) finalize_device(tot, A.n_global > 0 ? (double)A.n_global : tot[7], A.p, A.loss_out);
-            if (A.total_sums != nullptr) {  // every block has read gsums long before the last one gets here
-#pragma unroll
-                for (int k = 0; k < PIL_NSUMS; ++k) A.total_sums[k] = tot[k];
-            }
+    // the loss from (global pointwise sums + global stencil sums), src/loss.py:134-160: the four quotients are formed
+    // by four threads side by side (same operations, same roundings as finalize_device)
+    if (wants_total && finalize && threadIdx.x < 32) {
+        if (threadIdx.x < PIL_NSUMS) {
+            const double tk = g_k + s_glob[threadIdx.x];
+            s_tot[threadIdx.x] = tk;
+            if (A.total_sums != nullptr) A.total_sums[threadIdx.x] = tk;  // every block has read gsums long before the last one gets here
         }
-        if (A.task_counter != nullptr) *A.task_counter = 0u;  // every warp has made its last claim
-        *A.ticket = 0u;
-        if (A.X.world > 0) xchg_advance_epoch(A.X);  // device-epoch mode: this rank has completed the step
+        __syncwarp();
+        if (A.loss_out != nullptr) {
+            const double n = A.n_global > 0 ? (double)A.n_global : s_tot[7];
+            if (threadIdx.x < 4) s_term[threadIdx.x] = finalize_term(s_tot, n, A.p, (int)threadIdx.x);
+            __syncwarp();
+            if (threadIdx.x == 0) finalize_from_terms(s_term, s_tot, A.p, A.loss_out);
+        }
     }
+    TL_STAMP(1, 6);  // last block only: loss assembled
+    if (threadIdx.x == 0 && A.X.world > 0) xchg_advance_epoch(A.X);  // device-epoch mode: this rank has completed the step
 }
 
 // TMA (ALIGNED only): the rows travel as 2-D tensor-map boxes (cp.async.bulk.tensor, one elected lane per warp, an
@@ -780,7 +790,7 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
             out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
         }
         out->rows = dyn_rows > 0 ? dyn_rows : (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
-        if (a.accumulate && (size_t)out->blocks * 2 * sizeof(double) > out->partials_avail) {
+        if (a.accumulate && (size_t)out->blocks * 2 * kPartialBytes > out->partials_avail) {
             out->status = PIL_ERR_WORKSPACE;
             return cudaSuccess;
         }

@@ -504,6 +504,27 @@ struct BwdArgs {
                            // the stencil sums (phase 1) and finalises the GLOBAL loss
 };
 
+// The loss from the sums, src/loss.py:134-160, in two steps so that the four quotients can be formed by four threads
+// side by side (the backward's last block: serial time at the end of the step): term 0 dice_loss, 1 bce, 2 rd, 3 pf.
+__device__ __forceinline__ double finalize_term(const double* s, double n, const PilParams& p, int k) {
+    if (k == 0) return 1.0 - (2.0 * s[0] + p.smooth) / (s[1] + s[2] + p.smooth);
+    return s[2 + k] / n;
+}
+__device__ __forceinline__ void finalize_from_terms(const double* term, const double* s, const PilParams& p, float* out) {
+    const double dice_loss = term[0], bce = term[1], rd = term[2], pf = term[3];
+    double total = p.dice_weight * dice_loss + p.bce_weight * bce;
+    if (p.pde_weight > 0.0) total += p.pde_weight * rd;
+    if (p.phase_field_weight > 0.0) total += p.phase_field_weight * pf;
+    if (s[6] > 0.0) total = __longlong_as_double(0x7ff8000000000000LL);  // see finalize_device
+    out[0] = (float)total;
+    out[1] = (float)dice_loss;
+    out[2] = (float)bce;
+    out[3] = (float)rd;
+    out[4] = (float)pf;
+    out[5] = (float)s[6];
+    out[6] = 0.f;
+    out[7] = 0.f;
+}
 __device__ __forceinline__ void finalize_device(const double* s, double n, const PilParams& p, float* out) {
     // src/loss.py:134-160
     const double I = s[0], P = s[1], T = s[2];
@@ -624,7 +645,7 @@ __device__ __forceinline__ void xchg_push(const XchgDev& X, int phase, const dou
 // vectors of `phase` in the LOCAL mailbox and adds them in rank order into out[0..7] (shared memory).
 // On timeout the sums are NaN, the mailbox status word is set and the function returns false (block-uniform):
 // the backward then writes a ZERO gradient, so a rank that lost its peers cannot poison the weights.
-static __device__ __noinline__ bool xchg_wait_sum(const XchgDev& X, int phase, double* out) {
+static __device__ __forceinline__ bool xchg_wait_sum(const XchgDev& X, int phase, double* out) {
     __shared__ unsigned int s_half[PIL_MAX_RANKS * kSlotWords];
     __shared__ int s_bad;
     const int i = (int)threadIdx.x;
@@ -664,73 +685,87 @@ static __device__ __noinline__ bool xchg_wait_sum(const XchgDev& X, int phase, d
 }
 
 // ------------------------------------------------------------------------------------------------
-// Deterministic two-level reduction of the 8 per-thread accumulators:
+// Deterministic two-level reduction of the per-thread accumulators:
 //   warp shuffles -> per-block doubles in `partials` -> the LAST block to finish (ticket) adds all
 //   per-block partials in a fixed order, so the result does not depend on block scheduling.
-// Returns true in the last block only; there thread 0 holds the totals in out[].  The caller resets
-// *ticket to 0 when it is done (so the workspace is reusable by the next launch on the stream).
+// Returns true in the last block only; there thread 0 holds the totals in out[].
 // accumulator layout: 0 I, 1 P, 2 T, 3 bce (log2 units, un-negated), 4 r^2, 5 dx^2+dy^2, 6 (uv)^2, 7 #invalid
+//
+// No fence on the way.  This is serial time at the very end of a kernel (the next kernel of the stream waits for it), and
+// a __threadfence() there first waits for every gradient store the thread still has in flight (1.3-1.7 us in the backward,
+// tools/timeline.py).  Instead every partial travels self-validating, like the peer mailbox words above: a double is two
+// 8-byte words {32 payload bits, 32-bit tag of THIS launch}, a naturally aligned 8-byte store is single-copy atomic, and
+// the last block re-reads a word until it carries the tag (only stores that left just before the last ticket can still be
+// in flight).  The tag comes with the ticket: the 64-bit word {reduction epoch, blocks arrived} at header words 2-3 is
+// incremented by every block, so each block learns the epoch from its own atomic, consistently (no block of this launch
+// can see the value the last block leaves behind: {epoch + 1, 0}).  Stale slots carry the tags of earlier epochs or the
+// zero of pil_workspace_init, never the current one.
+// Workspace header (unsigned int, relative to `ticket`): [0] ticket of the kernels that keep their own scheme,
+// [1] task counter, [2..3] {blocks arrived, reduction epoch}; the WHOLE workspace is zero before first use.
 // ------------------------------------------------------------------------------------------------
+constexpr int kWsRedWord = 2;
+constexpr size_t kPartialBytes = 16;  // bytes one double occupies in the partials area
+__device__ __forceinline__ ulonglong2 partial_load(const ulonglong2* p) {
+    ulonglong2 w;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w.x), "=l"(w.y) : "l"(p) : "memory");
+    return w;
+}
 // second level: the block's N doubles (thread k < N holds component k in `blk`) -> `partials` -> the LAST block to
-// finish (ticket) adds all blocks' partials in a fixed order.  Returns true in the last block only; there thread 0
-// holds the totals in out[].  The caller resets *ticket to 0 when it is done.
+// finish adds all blocks' partials in a fixed order.  Every warp of the block has finished its work when this is called
+// (the callers synchronise before forming `blk`).  Returns true in the last block only; there thread 0 holds the
+// totals in out[], and the header is already set for the next launch.
 template <int THREADS, int N, int TLK = -1>
 __device__ __forceinline__ bool blocks_to_last(double blk, double* partials, unsigned int* ticket, double* out) {
     constexpr int kWarps = THREADS / 32;
-    constexpr int NP = N / 2;  // component pairs (16-byte loads)
-    static_assert(N % 2 == 0 && THREADS % NP == 0 && (NP & (NP - 1)) == 0 && NP <= 32 && 32 % NP == 0, "component layout");
+    static_assert((N & (N - 1)) == 0 && N <= 32 && THREADS % N == 0, "component layout");
     __shared__ double s_red[kWarps * N];
     __shared__ double s_tot[N];
-    __shared__ bool s_last;
+    __shared__ unsigned long long s_old;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(ticket + kWsRedWord);
     if constexpr (TLK >= 0) TL_STAMP(TLK, 4);  // every warp of the block has arrived
+    if (threadIdx.x == 0) s_old = atomicAdd(red, 1ull);
+    __syncthreads();
+    const unsigned long long old = s_old;
+    const unsigned int epoch = (unsigned int)(old >> 32);
+    const unsigned long long tag = (unsigned long long)(epoch % 0xfffffffeu + 1u) << 32;
     if (threadIdx.x < N) {
-        partials[(long long)blockIdx.x * N + threadIdx.x] = blk;
-        __threadfence();
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(blk);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(partials) + (long long)blockIdx.x * N + threadIdx.x;
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"((bits & 0xffffffffull) | tag), "l"((bits >> 32) | tag)
+                     : "memory");
     }
-    __syncthreads();
-    if constexpr (TLK >= 0) TL_STAMP(TLK, 5);  // partial written and fenced
-    if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(ticket, 1u);
-        s_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if constexpr (TLK >= 0) TL_STAMP(TLK, 6);  // ticket taken
-    if (!s_last) return false;
-    __threadfence();
-    constexpr int kGroups = THREADS / NP;
+    if constexpr (TLK >= 0) TL_STAMP(TLK, 5);  // ticket taken, partial sent
+    if ((unsigned int)old != gridDim.x - 1) return false;
+    if (threadIdx.x == 0) *red = (unsigned long long)(epoch + 1u) << 32;  // every block has arrived: ready for the next launch
+    constexpr int kGroups = THREADS / N;
     {
-        // kGroups block-groups x NP component PAIRS: 16-byte L2 loads, 8 in flight per thread (the tail
-        // batch is predicated, not serialised), fixed order -> bit-reproducible.  This is serial time
-        // at the very end of the kernel, so it is kept to 2-3 L2 round trips.
-        constexpr int kIlp = 8;
-        const int c2 = threadIdx.x % NP, j = threadIdx.x / NP;
+        // kGroups block-groups x N components: 16-byte L2 loads, kIlp in flight per thread (the tail batch is
+        // predicated, not serialised), fixed order -> bit-reproducible; 1-2 L2 round trips for the usual grids
+        constexpr int kIlp = N >= 8 ? 10 : 8;
+        const int c = threadIdx.x % N, j = threadIdx.x / N;
         const long long nb = gridDim.x;
-        double vx = 0.0, vy = 0.0;
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(partials) + c;
+        double v = 0.0;
         for (long long b0 = j; b0 < nb; b0 += (long long)kIlp * kGroups) {
-            double2 w[kIlp];
+            ulonglong2 w[kIlp];
 #pragma unroll
             for (int q = 0; q < kIlp; ++q) {
                 const long long b = b0 + (long long)q * kGroups;
-                w[q] = (b < nb) ? __ldcg(reinterpret_cast<const double2*>(partials + b * N) + c2) : make_double2(0.0, 0.0);
+                w[q] = (b < nb) ? partial_load(src + b * N) : make_ulonglong2(tag, tag);
             }
 #pragma unroll
             for (int q = 0; q < kIlp; ++q) {
-                vx += w[q].x;
-                vy += w[q].y;
+                while ((((w[q].x ^ tag) | (w[q].y ^ tag)) >> 32) != 0ull)  // still in flight
+                    w[q] = partial_load(src + (b0 + (long long)q * kGroups) * N);
+                v += __longlong_as_double((long long)((w[q].x & 0xffffffffull) | (w[q].y << 32)));
             }
         }
-        // threads with the same lane % NP hold partial sums of the same component pair: butterfly over the other
-        // lane bits (fixed pattern -> bit-reproducible), then one value per warp and pair through shared memory
+        // threads with the same lane % N hold partial sums of the same component: butterfly over the other
+        // lane bits (fixed pattern -> bit-reproducible), then one value per warp and component through shared memory
 #pragma unroll
-        for (int o = 16; o >= NP; o >>= 1) {
-            vx += __shfl_xor_sync(0xffffffffu, vx, o);
-            vy += __shfl_xor_sync(0xffffffffu, vy, o);
-        }
-        if (lane < NP) {
-            s_red[(warp * NP + lane) * 2] = vx;  // s_red viewed as [kWarps][N]
-            s_red[(warp * NP + lane) * 2 + 1] = vy;
-        }
+        for (int o = 16; o >= N; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < N) s_red[warp * N + lane] = v;
     }
     __syncthreads();
     if (threadIdx.x < N) {
@@ -744,6 +779,7 @@ __device__ __forceinline__ bool blocks_to_last(double blk, double* partials, uns
 #pragma unroll
         for (int k = 0; k < N; ++k) out[k] = s_tot[k];
     }
+    if constexpr (TLK >= 0) TL_STAMP(TLK, 4);  // last block only (overwrites its arrival stamp): every block's partials added
     return true;
 }
 

@@ -400,7 +400,7 @@ static cudaError_t launch_fwd_a(FwdArgs& a, int64_t B, int64_t H, int64_t W, boo
             out->blocks = (int)((a.g.tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
         }
         out->rows = (int)((a.g.total_rows + a.g.groups - 1) / a.g.groups);
-        if ((size_t)out->blocks * (moments ? 16 : PIL_NSUMS) * sizeof(double) > partial_bytes_avail) {
+        if ((size_t)out->blocks * (moments ? 16 : PIL_NSUMS) * kPartialBytes > partial_bytes_avail) {
             out->status = PIL_ERR_WORKSPACE;
             return cudaSuccess;
         }

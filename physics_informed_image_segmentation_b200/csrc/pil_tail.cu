@@ -286,7 +286,8 @@ extern "C" {
 size_t pil_tail_workspace_bytes(int64_t C) {
     if (C < 1 || C > kTailMaxC) return 0;
     // ticket + partials of the forward sums (8 doubles per block) and of the backward (C + 1 doubles per block)
-    return 256 + (size_t)kMaxPointBlocks * (size_t)(C + 1 > PIL_NSUMS ? C + 1 : PIL_NSUMS) * sizeof(double);
+    // (the forward's partials are tagged 16-byte slots, pil_common.cuh)
+    return 256 + (size_t)kMaxPointBlocks * (size_t)(C + 1 > 2 * PIL_NSUMS ? C + 1 : 2 * PIL_NSUMS) * sizeof(double);
 }
 
 int pil_tail_forward(const void* feat, int feat_dtype, const float* weight, const float* bias, const void* t, int t_dtype, int64_t B,

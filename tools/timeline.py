@@ -25,6 +25,7 @@ ap.add_argument("--workload", default="cfg3")
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--side-stream", action="store_true")
 ap.add_argument("--shape", default="", help="BxHxW instead of a named workload")
+ap.add_argument("--graph", action="store_true", help="steps are CUDA-graph launches (no host gaps); the stamps are those of the last one")
 a = ap.parse_args()
 B, H, W, name = bench.WORKLOADS[a.workload]
 if a.shape:
@@ -47,8 +48,21 @@ with torch.cuda.stream(stream):
         Fn.forward_pointwise(z, t, p, 1, sums=sums)
         Fn.backward_accumulate(z, t, p, 1, sums, z.numel(), out=g, stencil_sums=sb, report=rep)
     torch.cuda.synchronize()
+    if a.graph:
+        sg = Fn.StepGraph(z, t, p, 1, grad=g)
+        for _ in range(3):
+            sg.launch()
+        assert L.pil_debug_timeline(tl[a.steps - 1].data_ptr()) == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_rep = 50
+        e0.record()
+        for _ in range(n_rep):
+            sg.launch()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"graph launches: {e0.elapsed_time(e1) * 1e3 / n_rep:.1f} us per step")
     # one buffer per step, the pointer is switched by a tiny async symbol copy between steps
-    for k in range(a.steps):
+    for k in range(0 if a.graph else a.steps):
         assert L.pil_debug_timeline(tl[k].data_ptr()) == 0
         Fn.forward_pointwise(z, t, p, 1, sums=sums)
         Fn.backward_accumulate(z, t, p, 1, sums, z.numel(), out=g, stencil_sums=sb, report=rep)
@@ -66,14 +80,20 @@ for ker in range(2):
     print(f"  {names[ker]:14s} entry {ent.min():7.1f}..{ent.max():7.1f} | after wait {wait.min():7.1f}..{wait.max():7.1f} | "
           f"loop end {loop.min():7.1f}..{loop.max():7.1f} (p50 {np.median(loop):7.1f}, p95 {np.percentile(loop, 95):7.1f}) | exit max {ex.max():7.1f}")
     if ker == 1 and X.shape[0] and T[k, ker, :nb[ker], 4].max() > 0:
-        Y = (T[k, ker, :nb[ker], 4:7] - t0) / 1e3
-        print(f"      epilogue: all warps of the block arrived {Y[:, 0].min():7.1f}..{Y[:, 0].max():7.1f} | partial written + fenced "
-              f"+{np.median(Y[:, 1] - Y[:, 0]):.2f} (max +{(Y[:, 1] - Y[:, 0]).max():.2f}) | ticket +{np.median(Y[:, 2] - Y[:, 1]):.2f} "
-              f"(max +{(Y[:, 2] - Y[:, 1]).max():.2f}) | last block: ticket at {Y[:, 2].max():7.1f}, exit {ex.max():7.1f}")
+        # stamps 4: every warp of the block arrived (the LAST block re-stamps it when all partials are added),
+        # 5: ticket taken + partial sent, 6: loss assembled (last block only)
+        lb = int(np.argmax(T[k, ker, :nb[ker], 3]))
+        Y = (T[k, ker, :nb[ker], 4:6] - t0) / 1e3
+        oth = np.arange(nb[ker]) != lb
+        if oth.any():
+            print(f"      epilogue: block arrived -> ticket taken, partial sent +{np.median((Y[:, 1] - Y[:, 0])[oth]):.2f} us "
+                  f"(max +{(Y[:, 1] - Y[:, 0])[oth].max():.2f})")
+        Z = (T[k, ker, lb, :8] - t0) / 1e3
+        print(f"      last block {lb}: loop end {Z[2]:.1f} | ticket taken {Z[5]:.1f} | partials added {Z[4]:.1f} | loss assembled {Z[6]:.1f} | exit {Z[3]:.1f}")
     smid = T[k, ker, :nb[ker], 7]
     dur = loop - wait
     print(f"      main-loop duration per block: min {dur.min():.1f} p50 {np.median(dur):.1f} p95 {np.percentile(dur, 95):.1f} max {dur.max():.1f} us; "
           f"{len(np.unique(smid))} SMs")
-if a.steps > 1:
+if a.steps > 1 and not a.graph:
     prev_exit = (T[k - 1, 1, :nb[1], 3].max() - t0) / 1e3
     print(f"  previous step's backward exit at {prev_exit:.1f} us; step period {(t0 - T[k - 1, 0, :nb[0], 0].min()) / 1e3:.1f} us")
