@@ -711,22 +711,28 @@ __global__ void __launch_bounds__(kThreads, kBwdMinBlocks) pil_bwd_kernel_tma(co
     bwd_body<KIND, XT, TT, true, true>(A, &tmx, &tmt);
 }
 // Rows per dynamically claimed range of the backward kernel.  PIL_BWD_ROWS forces a value (0 = static
-// partition).  Automatic: 64 rows -- long enough to amortise the 4 halo rows and the pipeline fill of a
-// range, short enough to balance.  Measured on B200 at 64x1024^2 fp32: static 157.8 us; dynamic 24 rows
-// 169.9, 32: 157.5, 48: 155.6, 61: 149-153, 63: 150.5, 64: 145-147, 67: 152, 96: 149.5, 128: 155.7 (the
-// power of two wins over its neighbours: range boundaries then tile the 2 MB pages).  Shrinking ranges
-// (guided self-scheduling), a small-range tail phase and claiming one range ahead to prefetch it were all
-// measured slower.  Problems too small for ~2.5 waves of such ranges keep the static one-wave partition.
-static int bwd_dynamic_rows(long long total_rows, long long strips, long long resident_warps) {
+// partition).  Automatic: long enough to amortise the 4 halo rows and the pipeline fill of a range, short enough to
+// balance.  Measured on B200, 64x1024^2 / 128x2048^2, with the 10% tail phase below where it applies:
+//   fp32 maps: 24 rows 136.0 us / 973 us, 32: 135.1 / 1006, 40: 133.0 / 1012, 44: 137.2 / 1042, 48: 131.9 / 1004,
+//              52: 134.0 / 1031, 64: 134.9 / 1040, 96: 135.0, 128: 137.2                                  -> 48
+//   bf16 maps (bound by the FMA pipe: the halo rows' arithmetic is what costs): 64 rows 118.7 us / 845 us,
+//              96: 120.7 / 834, 112: 116.5 / 826, 128: 116.5 / 815, 144: 117.4 / 836, 192: 131.7 / 837, 256: 118.6 / 820 -> 128
+// Shrinking ranges (guided self-scheduling) and claiming one range ahead to prefetch it were measured slower.
+// Problems too small for a few waves of such ranges keep the static one-wave partition (32x512^2, 8x1024^2 and
+// 16x1024^2: static 38.5 / 36.7 / 63.4 us per step against 38.3-42.5 / 38.0-41.5 / 64.2-70.1 with 12..32-row ranges).
+static int bwd_dynamic_rows(long long total_rows, long long strips, long long resident_warps, bool narrow_maps) {
     static int forced = -2;
     if (forced == -2) {
         const char* e = getenv("PIL_BWD_ROWS");
         forced = e ? atoi(e) : -1;
     }
     if (forced >= 0) return (forced > 0 && forced < kMinRows) ? kMinRows : forced;
-    const int rows = 64;
-    const double waves = (double)(((total_rows + rows - 1) / rows) * strips) / (double)resident_warps;
-    return waves < 2.5 ? 0 : rows;
+    auto waves = [&](int rows) { return (double)(((total_rows + rows - 1) / rows) * strips) / (double)resident_warps; };
+    if (narrow_maps) {
+        if (waves(128) >= 1.5) return 128;
+        return waves(64) < 2.5 ? 0 : 64;
+    }
+    return waves(48) < 2.5 ? 0 : 48;
 }
 // How the aligned backward stages its rows: 1 = TMA boxes (cp.async.bulk.tensor + mbarrier), 0 = per-lane cp.async.
 // pil_set_bwd_staging() / PIL_BWD_STAGE=tma|cpasync override the default.
@@ -752,7 +758,7 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
         const int resident = sm_count() * per_sm;
         const long long strips_ = (W + kStripCols - 1) / kStripCols;
         const int dyn_rows = a.task_counter != nullptr
-                                 ? (tune_rps > 0 ? tune_rps : bwd_dynamic_rows(B * H, strips_, (long long)resident * kWarpsPerBlock))
+                                 ? (tune_rps > 0 ? tune_rps : bwd_dynamic_rows(B * H, strips_, (long long)resident * kWarpsPerBlock, sizeof(XT) == 2))
                                  : 0;
         if (dyn_rows > 0) {
             // persistent grid of the resident blocks; short ranges claimed dynamically (see the kernel)
@@ -766,8 +772,9 @@ static cudaError_t launch_bwd_a(BwdArgs& a, int64_t B, int64_t H, int64_t W, boo
                 tail_pct = pc < 0 ? 0 : (pc > 90 ? 90 : pc);
                 tail_range = r < 0 ? 0 : r;
             }
-            // (measured at 64x1024^2, three interleaved repetitions: fp32 145.2-145.3 us against 147.3-148.1 without; bf16 maps,
-            // bound by the FMA pipe rather than by the last ranges' memory latency, 135.0 against 133.1: fp32 maps only)
+            // (measured at 64x1024^2 / 128x2048^2 with 48-row ranges, two interleaved repetitions: fp32 131.9 us / 1004 us against
+            // 135.0-135.2 / 1009-1012 without, 24-row tail ranges 133.0 / 997-1004; bf16 maps, bound by the FMA pipe rather
+            // than by the last ranges' memory latency, lose 2 us: fp32 maps only)
             if (tail_range >= kMinRows && tail_pct > 0 && tail_range < dyn_rows && sizeof(XT) == 4) {
                 long long tr = (long long)B * H * tail_pct / 100;
                 tr -= tr % tail_range;
