@@ -809,6 +809,23 @@ def run_sweep(args, C: Ctx):
                 C.dist.all_reduce(moments)
             Fn.sweep_finalize(moments, n_global, grid, reports=reports)
 
+    # timed steps: one CUDA-graph launch each (pil_sweep_graph_*) for shards up to 16 Mpixel -- a sharded pass takes a few
+    # tens of microseconds, less than the host needs for two calls (8 ranks: 85 us per step direct against the 38 us the
+    # kernel takes); the per-kernel event pass above stays on direct calls
+    use_graph = args.launch == "graph" or (args.launch == "auto" and n_local <= (16 << 20))
+    if C.distributed and X.device is None:
+        use_graph = False
+    graphs = []
+    if use_graph:
+        graphs = [Fn.SweepGraph(zz, tt, kind, grid, exchange=X.device, n_global=n_global) for zz, tt in sets]
+
+    def timed_step():
+        if graphs:
+            state["k"] += 1
+            graphs[state["k"] % n_sets].launch()
+        else:
+            step()
+
     sampler = ClockSampler(C.local_rank)
     if C.rank == 0:
         sampler.start()
@@ -832,6 +849,7 @@ def run_sweep(args, C: Ctx):
             raise SystemExit(3)
     for _ in range(max(args.warmup, 3)):
         step()
+        timed_step()
     C.barrier()
     K = args.steps
     KA = max(3, min(K, 30))
@@ -845,11 +863,13 @@ def run_sweep(args, C: Ctx):
     C.barrier()
     e0.record()
     for _ in range(K):
-        step()
+        timed_step()
     e1.record()
     torch.cuda.synchronize()
     C.barrier()
-    launches = Fn.launch_info().kernels_launched - k0
+    launches = (2 * K) if graphs else Fn.launch_info().kernels_launched - k0   # a graph launch replays the two kernels
+    if graphs:
+        reports = graphs[state["k"] % n_sets].reports
     total_ms = C.max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if C.rank == 0 else None
     if C.rank == 0:
@@ -866,6 +886,7 @@ def run_sweep(args, C: Ctx):
                        "step": ("pil_forward_moments_xchg (one pass over x, t; the shard's 16 sums pushed into every rank's mailbox) -> "
                                 "pil_sweep_finalize_xchg (11 global loss reports)") if X.host is not None else
                                "pil_forward_moments (one pass over x, t) -> all-reduce of 16 doubles -> pil_sweep_finalize (11 loss reports)",
+                       "launch": "one CUDA-graph launch per step (pil_sweep_graph_*)" if graphs else "two direct C-ABI calls per step",
                        "l2_policy": ("maps %.0f MB per step > 2 x 126 MB L2" % (footprint / 1e6)) if n_sets == 1 else
                                     ("maps %.1f MB per step: steps rotate through %d buffer sets" % (footprint / 1e6, n_sets))},
             "pixel_evaluations_per_s": value * len(grid) * 1e9,
@@ -875,6 +896,8 @@ def run_sweep(args, C: Ctx):
             "gpu_launches": int(launches), "clocks": clocks, "losses": [float(v) for v in reports[:, 0].cpu()],
             "exchange_timeout": X.timed_out(), **({"parity": parity} if parity else {}),
         })
+    for gsw in graphs:
+        gsw.close()
     X.close()
 
 

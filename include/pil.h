@@ -273,7 +273,9 @@ int pil_sweep_finalize(const double* moments, int64_t n_global, const PilParams*
  * the shard's 16 sums into every rank's mailbox (two 8-double vectors, phases 0 and 1 of the PilExchange below);
  * pil_sweep_finalize_xchg waits for all ranks' vectors in the LOCAL mailbox, adds them in rank order and writes the
  * n_params (<= 32) loss reports of the GLOBAL batch, identical on every rank (moments_out: the global moments, may be
- * NULL).  Same epoch discipline as the training step (one epoch per sweep step, host epochs only). */
+ * NULL).  Same epoch discipline as the training step: one epoch per sweep step; with PIL_XCHG_DEVICE_EPOCH the
+ * finalize kernel completes the step (it advances the mailbox counter), so every pil_forward_moments_xchg must be
+ * followed by its pil_sweep_finalize_xchg. */
 int pil_forward_moments_xchg(const void* x, const void* t, int64_t B, int64_t H, int64_t W,
                              int x_dtype, int t_dtype, int x_kind,
                              double* moments, void* workspace, size_t workspace_bytes,
@@ -364,6 +366,15 @@ int pil_step_graph_create(PilStepGraph** out, const void* x, const void* t, void
                           double* total_sums, void* stream);
 int pil_step_graph_launch(PilStepGraph* g, void* stream);
 int pil_step_graph_destroy(PilStepGraph* g);
+/* The sweep step (pil_forward_moments[_xchg] -> pil_sweep_finalize[_xchg]) as one graph launch: a sharded sweep leaves
+ * each GPU a pass of a few tens of microseconds, less than the host needs for two calls.  Same rules as above (bound to
+ * x, t, moments, workspace, loss_out, moments_out; ex NULL or with PIL_XCHG_DEVICE_EPOCH; creation runs one real sweep
+ * step and is collective).  params (HOST, n_params settings; <= 32 with ex) are copied into the graph.  Launch and
+ * destroy with pil_step_graph_launch / pil_step_graph_destroy. */
+int pil_sweep_graph_create(PilStepGraph** out, const void* x, const void* t, int64_t B, int64_t H, int64_t W,
+                           int x_dtype, int t_dtype, int x_kind, double* moments, void* workspace, size_t workspace_bytes,
+                           const struct PilExchange* ex, int64_t n_global, const PilParams* params, int n_params,
+                           float* loss_out, double* moments_out, void* stream);
 
 /*
  * The PDERegularization operators a caller can use on their own (fp32 maps):

@@ -219,6 +219,11 @@ _SIGS = {
                                              ctypes.POINTER(PilParams), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(PilExchange), ctypes.c_int64,
                                              ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "pil_sweep_graph_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(PilExchange),
+                                              ctypes.c_int64, ctypes.POINTER(PilParams), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p]),
     "pil_step_graph_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "pil_step_graph_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pil_boundary_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64] * 3),

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kThreads) pil_sweep_finalize_xchg_kernel(XchgD
     const bool ok1 = xchg_wait_sum(X, 1, s_mo + 8);
     (void)ok0;
     (void)ok1;  // a timed-out wait leaves NaN moments: every loss of the sweep is NaN and the status word is set
+    if (threadIdx.x == 0) xchg_advance_epoch(X);  // device-epoch mode: this rank has completed the sweep step
     if (moments_out != nullptr && threadIdx.x < 16) moments_out[threadIdx.x] = s_mo[threadIdx.x];
     const int k = threadIdx.x;
     if (k >= sp.n) return;
@@ -422,7 +423,6 @@ int pil_forward_moments(const void* x, const void* t, int64_t B, int64_t H, int6
 int pil_forward_moments_xchg(const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype, int x_kind,
                              double* moments, void* workspace, size_t workspace_bytes, const PilExchange* ex, void* stream) {
     if (!ex) return PIL_ERR_NULL;
-    if (ex->flags & PIL_XCHG_DEVICE_EPOCH) return PIL_ERR_EXCHANGE;  // the sweep has no backward to advance the counter
     PilParams neutral = {0.5, 0.5, 0.0, 0.0, 1.0, 0.5, 1.0, 1e-6};
     return forward_impl(x, t, B, H, W, x_dtype, t_dtype, x_kind, &neutral, moments, nullptr, workspace, workspace_bytes, stream, true, ex);
 }
@@ -438,7 +438,6 @@ int pil_sweep_finalize_xchg(const PilExchange* ex, int64_t n_global, const PilPa
     XchgDev X;
     int st = make_xchg(ex, &X);
     if (st != PIL_OK) return st;
-    if (X.device_epoch) return PIL_ERR_EXCHANGE;
     SweepParams sp;
     sp.n = n_params;
     for (int k = 0; k < n_params; ++k) sp.p[k] = params[k];

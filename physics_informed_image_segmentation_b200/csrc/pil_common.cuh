@@ -742,7 +742,7 @@ __device__ __forceinline__ bool blocks_to_last(double blk, double* partials, uns
     {
         // kGroups block-groups x N components: 16-byte L2 loads, kIlp in flight per thread (the tail batch is
         // predicated, not serialised), fixed order -> bit-reproducible; 1-2 L2 round trips for the usual grids
-        constexpr int kIlp = N >= 8 ? 10 : 8;
+        constexpr int kIlp = N >= 16 ? 14 : (N >= 8 ? 10 : 8);
         const int c = threadIdx.x % N, j = threadIdx.x / N;
         const long long nb = gridDim.x;
         const ulonglong2* src = reinterpret_cast<const ulonglong2*>(partials) + c;

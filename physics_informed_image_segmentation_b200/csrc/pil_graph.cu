@@ -63,6 +63,64 @@ int enqueue_step(const StepArgs& a, cudaStream_t s) {
                                    a.grad_scale, a.stencil_sums, a.loss_out, a.workspace, a.workspace_bytes, s);
 }
 
+// the sweep step (BASELINE config 4): one pass for the moments, one block for the n_params loss reports
+struct SweepArgs {
+    const void* x;
+    const void* t;
+    int64_t B, H, W;
+    int x_dtype, t_dtype, x_kind;
+    double* moments;
+    void* workspace;
+    size_t workspace_bytes;
+    const PilExchange* ex;
+    int64_t n_global;
+    const PilParams* params;
+    int n_params;
+    float* loss_out;
+    double* moments_out;
+};
+int enqueue_sweep(const SweepArgs& a, cudaStream_t s) {
+    if (a.ex != nullptr) {
+        const int st = pil_forward_moments_xchg(a.x, a.t, a.B, a.H, a.W, a.x_dtype, a.t_dtype, a.x_kind, a.moments, a.workspace,
+                                                a.workspace_bytes, a.ex, s);
+        if (st != PIL_OK) return st;
+        return pil_sweep_finalize_xchg(a.ex, a.n_global, a.params, a.n_params, a.loss_out, a.moments_out, s);
+    }
+    const int st = pil_forward_moments(a.x, a.t, a.B, a.H, a.W, a.x_dtype, a.t_dtype, a.x_kind, a.moments, a.workspace, a.workspace_bytes, s);
+    if (st != PIL_OK) return st;
+    return pil_sweep_finalize(a.moments, a.n_global, a.params, a.n_params, a.loss_out, s);
+}
+
+// run `enqueue` once for real on the caller's stream (validates, fills the per-device caches outside of capture and -- data
+// parallel -- is a step like any other), then capture it on a private stream and instantiate
+template <typename F>
+int capture_graph(PilStepGraph** out, F enqueue, cudaStream_t user) {
+    int st = enqueue(user);
+    if (st != PIL_OK) return st;
+    cudaError_t e = cudaStreamSynchronize(user);
+    if (e != cudaSuccess) return (int)e;
+    PilStepGraph* g = new (std::nothrow) PilStepGraph();
+    if (!g) return (int)cudaErrorMemoryAllocation;
+    *g = PilStepGraph{};
+    cudaGetDevice(&g->device);
+    e = cudaStreamCreateWithFlags(&g->capture_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamBeginCapture(g->capture_stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        pil_step_graph_destroy(g);
+        return (int)e;
+    }
+    st = enqueue(g->capture_stream);
+    e = cudaStreamEndCapture(g->capture_stream, &g->graph);  // always end the capture, also after a failed enqueue
+    if (st == PIL_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (st != PIL_OK || e != cudaSuccess) {
+        pil_step_graph_destroy(g);
+        cudaGetLastError();
+        return st != PIL_OK ? st : (int)e;
+    }
+    *out = g;
+    return PIL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -85,35 +143,20 @@ int pil_step_graph_create(PilStepGraph** out, const void* x, const void* t, void
     if (ex != nullptr && !(ex->flags & PIL_XCHG_DEVICE_EPOCH)) return PIL_ERR_EXCHANGE;  // a host epoch would be frozen into the graph
     StepArgs a = {x, t, grad, B, H, W, x_dtype, t_dtype, x_kind, *p, sums, loss_out, workspace, workspace_bytes, ex, n_global,
                   upstream, grad_scale, stencil_sums, total_sums};
-    // One real step first, on the caller's stream: it validates the arguments, fills the library's per-device caches
-    // (occupancy, shared-memory attributes, the TMA encoder) outside of stream capture, and -- data parallel -- is a
-    // step like any other, taken by every rank (creation is collective).
-    cudaStream_t user = (cudaStream_t)stream;
-    int st = enqueue_step(a, user);
-    if (st != PIL_OK) return st;
-    cudaError_t e = cudaStreamSynchronize(user);
-    if (e != cudaSuccess) return (int)e;
+    // One real step first, on the caller's stream (data parallel: taken by every rank -- creation is collective), then
+    // the capture: see capture_graph.
+    return capture_graph(out, [&](cudaStream_t s) { return enqueue_step(a, s); }, (cudaStream_t)stream);
+}
 
-    PilStepGraph* g = new (std::nothrow) PilStepGraph();
-    if (!g) return (int)cudaErrorMemoryAllocation;
-    *g = PilStepGraph{};
-    cudaGetDevice(&g->device);
-    e = cudaStreamCreateWithFlags(&g->capture_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamBeginCapture(g->capture_stream, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) {
-        pil_step_graph_destroy(g);
-        return (int)e;
-    }
-    st = enqueue_step(a, g->capture_stream);
-    e = cudaStreamEndCapture(g->capture_stream, &g->graph);  // always end the capture, also after a failed enqueue
-    if (st == PIL_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
-    if (st != PIL_OK || e != cudaSuccess) {
-        pil_step_graph_destroy(g);
-        cudaGetLastError();
-        return st != PIL_OK ? st : (int)e;
-    }
-    *out = g;
-    return PIL_OK;
+int pil_sweep_graph_create(PilStepGraph** out, const void* x, const void* t, int64_t B, int64_t H, int64_t W, int x_dtype, int t_dtype,
+                           int x_kind, double* moments, void* workspace, size_t workspace_bytes, const PilExchange* ex,
+                           int64_t n_global, const PilParams* params, int n_params, float* loss_out, double* moments_out,
+                           void* stream) {
+    if (!out || !x || !t || !moments || !workspace || !params || !loss_out) return PIL_ERR_NULL;
+    if (ex != nullptr && !(ex->flags & PIL_XCHG_DEVICE_EPOCH)) return PIL_ERR_EXCHANGE;  // a host epoch would be frozen into the graph
+    const SweepArgs a = {x, t, B, H, W, x_dtype, t_dtype, x_kind, moments, workspace, workspace_bytes, ex, n_global, params, n_params,
+                         loss_out, moments_out};
+    return capture_graph(out, [&](cudaStream_t s) { return enqueue_sweep(a, s); }, (cudaStream_t)stream);
 }
 
 int pil_step_graph_launch(PilStepGraph* g, void* stream) {

@@ -559,6 +559,61 @@ class StepGraph:
             pass
 
 
+class SweepGraph:
+    """One sweep step (forward_moments -> sweep_finalize[_xchg]: K loss reports from one pass over the maps) as ONE
+    CUDA-graph launch (include/pil.h pil_sweep_graph_create).  Bound to `x` and `t`: refill them in place between
+    launches.  With `exchange` (a sharding.PeerExchange created with device_epoch=True) x and t are this rank's shard
+    and the reports describe the GLOBAL batch; construction is then collective and performs one real sweep step.
+    `launch()` returns `reports` (float32[K, 8], device, no sync)."""
+
+    def __init__(self, x: torch.Tensor, t: torch.Tensor, kind: int, params: Sequence[LossParams], exchange=None, n_global: int = -1):
+        K = len(params)
+        if K < 1 or (exchange is not None and K > 32):
+            raise ValueError("need 1..32 parameter settings (any number >= 1 without an exchange)")
+        for p in params:
+            p.validate()
+        B, H, W = check_maps(x, t)
+        dev = x.device
+        self.x, self.t = x, t
+        self.moments = torch.empty(PIL_NMOMENTS, dtype=torch.float64, device=dev)          # this shard's
+        self.global_moments = torch.empty(PIL_NMOMENTS, dtype=torch.float64, device=dev) if exchange is not None else self.moments
+        self.reports = torch.empty(K, PIL_NOUT, dtype=torch.float32, device=dev)
+        self._ws = torch.zeros(max(_lib.lib().pil_workspace_bytes(B, H, W), 1 << 12), dtype=torch.uint8, device=dev)
+        self._ex = None
+        if exchange is not None:
+            if not getattr(exchange, "device_epoch", False):
+                raise ValueError("SweepGraph needs a PeerExchange created with device_epoch=True")
+            self._ex = exchange.next_step()
+            self._exchange = exchange  # keeps the mailboxes mapped
+        arr = (PilParams * K)(*[p.c() for p in params])
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            st = _lib.lib().pil_sweep_graph_create(
+                ctypes.byref(self._h), x.data_ptr(), t.data_ptr(), B, H, W, _x_dtype(x), _t_dtype(t), kind, self.moments.data_ptr(),
+                self._ws.data_ptr(), self._ws.numel(), ctypes.byref(self._ex) if self._ex is not None else None,
+                int(B * H * W if exchange is None else n_global), arr, K, self.reports.data_ptr(),
+                self.global_moments.data_ptr() if exchange is not None else None, _stream_ptr(dev))
+        _lib.check(st, "pil_sweep_graph_create")
+        self._dev = dev
+
+    def launch(self) -> torch.Tensor:
+        with torch.cuda.device(self._dev):
+            st = _lib.lib().pil_step_graph_launch(self._h, _stream_ptr(self._dev))
+        _lib.check(st, "pil_step_graph_launch")
+        return self.reports
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().pil_step_graph_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def scale_gradient(grad: torch.Tensor, upstream: torch.Tensor) -> torch.Tensor:
     """grad *= upstream on the device, in place; free when upstream == 1 (plain loss.backward())."""
     dev = grad.device

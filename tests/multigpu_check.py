@@ -134,6 +134,19 @@ def main():
     for gr in gathered:
         assert torch.equal(gr[:5], rep_g[:5]), "every rank holds the same global report"
     assert rel_max(graph.grad.cpu().numpy(), og[b0:b1]) < 1e-5
+    # the sharded parameter sweep as one graph launch per step over the same device-epoch exchange (training steps and
+    # sweep steps may share a mailbox: each completes the epoch it used)
+    sgw = Fn.SweepGraph(xs, ts, Fn.X_LOGITS_SIGMOID, grid, exchange=pxd, n_global=B * H * W)
+    for step in range(3):
+        rep_sw = sgw.launch().clone()
+    graph.launch()  # and a training step after it still sees consistent epochs
+    torch.cuda.synchronize()
+    assert torch.allclose(rep_sw[:, :5], sw_all[:, :5], rtol=2e-6, atol=0), ("sweep graph", rep_sw[:, 0], sw_all[:, 0])
+    gathered = [torch.empty_like(rep_sw) for _ in range(world)]
+    dist.all_gather(gathered, rep_sw)
+    for gr in gathered:
+        assert torch.equal(gr[:, :5], rep_sw[:, :5]), "every rank holds the same sweep reports"
+    sgw.close()
     # the host-buffer session over the same exchange: global report, gradient of the shard on the device
     with P.HostSession(b1 - b0, H, W, device=local) as sess:
         for step in range(2):

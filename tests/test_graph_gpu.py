@@ -64,3 +64,28 @@ def test_step_graph_with_upstream_and_scale(env):
     torch.cuda.synchronize()
     assert rel_max(g.grad.cpu().numpy(), 2.0 * grad_d.cpu().numpy()) < 1e-6
     g.close()
+
+
+@pytest.mark.parametrize("shape", [(8, 128, 128), (3, 37, 53), (4, 96, 512)])
+def test_sweep_graph_matches_direct_calls(env, shape):
+    """pil_sweep_graph_create: moments pass + K loss reports as one graph launch == the two direct calls, also after the
+    bound maps were refilled in place; and == the fused loss of each setting evaluated on its own."""
+    P, Fn, po, dev = env
+    grid = P.s2_grid() + P.s3_grid()
+    z, t = blob_inputs(*shape, seed=21)
+    x, tt = z.to(dev), t.to(dev)
+    g = Fn.SweepGraph(x, tt, Fn.X_LOGITS_SIGMOID, grid)
+    for step in range(3):
+        if step:
+            z2, t2 = iid_inputs(*shape, seed=30 + step)
+            x.copy_(z2.to(dev))
+            tt.copy_(t2.to(dev))
+        rep = g.launch().clone()
+        rep_d = Fn.sweep_finalize(Fn.forward_moments(x, tt, Fn.X_LOGITS_SIGMOID), -1, grid)
+        torch.cuda.synchronize()
+        assert torch.equal(rep[:, :6], rep_d[:, :6]), (step, rep[:, 0], rep_d[:, 0])
+    for k in (0, 5, 8):  # against the one-setting-at-a-time evaluation (another kernel, other summation order)
+        s1, r1 = Fn.forward_sums(x, tt, grid[k], Fn.X_LOGITS_SIGMOID)
+        for c in range(4):  # total, dice, bce, rd (the sweep reports pf only where its weight is > 0)
+            assert rel_scalar(rep[k, c].item(), r1[c].item()) < 1e-5, (k, c)
+    g.close()
