@@ -289,7 +289,7 @@ int pil_sweep_finalize_xchg(const struct PilExchange* ex, int64_t n_global, cons
  * exchange); the only coupling is the batch-global reductions of src/loss.py:134-141 and
  * src/pde.py:143,:210.  Instead of an NCCL all-reduce between the two kernels, the kernels exchange
  * their 8-double vectors themselves: the last block of pil_forward_pointwise_xchg stores the shard's
- * sums into every rank's mailbox (remote stores over NVLink + a release flag), every block of
+ * sums into every rank's mailbox (remote 8-byte stores over NVLink, each carrying the step's tag), every block of
  * pil_backward_accumulate_xchg waits on its LOCAL copy of the flags and adds the vectors in rank order
  * (bit-identical global sums on all ranks), and its last block swaps the stencil sums the same way
  * and finalises the GLOBAL loss report.  Two launches per step, no collective call, no host sync.

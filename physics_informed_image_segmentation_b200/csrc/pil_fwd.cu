@@ -324,7 +324,6 @@ __device__ __forceinline__ void fwd_body(const FwdArgs& A, [[maybe_unused]] cons
             if (A.loss_out != nullptr) finalize_device(s, s[7], A.p, A.loss_out);
         }
         if (A.task_counter != nullptr) *A.task_counter = 0u;  // every warp has made its last claim
-        *A.ticket = 0u;
     }
     if constexpr (MOMENTS) {
         if (A.X.world > 0) {  // data-parallel sweep: this shard's 16 sums go to every rank as two 8-double vectors

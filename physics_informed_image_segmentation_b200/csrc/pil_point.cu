@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(kPointThreads, 4) pil_point_kernel(const Point
             A.sums[k] = sv[k];
             s_push[k] = sv[k];
         }
-        *A.ticket = 0u;
     }
     if (A.X.world > 0) {  // data parallel: hand the shard's sums to every rank over NVLink
         __syncthreads();
@@ -238,7 +237,6 @@ __global__ void __launch_bounds__(kPointThreads, 3) pil_point_metrics_kernel(con
             A.sums[k] = sv[k];
             s_push[k] = sv[k];
         }
-        *A.ticket = 0u;
     }
     if (A.X.world > 0) {
         __syncthreads();

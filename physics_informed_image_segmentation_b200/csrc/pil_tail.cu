@@ -129,7 +129,6 @@ __global__ void __launch_bounds__(kTailThreads) pil_tail_fwd_kernel(const TailFw
             A.sums[k] = sv[k];
             s_push[k] = sv[k];
         }
-        *A.ticket = 0u;
     }
     if (A.X.world > 0) {
         __syncthreads();
