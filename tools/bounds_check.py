@@ -43,7 +43,8 @@ def carve(B, H, W, offset_elems=0):
 
 
 shapes = [(1, 2, 2), (2, 3, 5), (1, 7, 1001), (3, 127, 129), (2, 70, 1024), (5, 17, 36), (1, 33, 240), (4, 64, 248), (2, 256, 256),
-          (3, 100, 120), (2, 64, 124), (1, 1024, 8), (6, 8, 2048)]
+          (3, 100, 120), (2, 64, 124), (1, 1024, 8), (6, 8, 2048),
+          (48, 1024, 1000)]   # large enough for the automatic partition: dynamically claimed 48-row ranges + the 16-row tail phase
 p = P.LossParams(pde_weight=1e-4, phase_field_weight=1e-4, diffusion_coeff=5.0)
 errors()
 bad = 0
